@@ -1,0 +1,185 @@
+/*
+ *  usearch_b200.h — C ABI of the B200-native batched HNSW search backend.
+ *
+ *  The library (usearch_b200/libusearch_b200.so) is a drop-in for the SEARCH path of the
+ *  reference's C ABI. Every `usearch_*` symbol below has the name, argument order, argument
+ *  meaning and error convention of the declaration it replaces in the reference header
+ *  `c/usearch.h` (cited per function as usearch.h:LINE, implementation c/lib.cpp:LINE), so that
+ *  Go (golang/lib.go:29-33), C# (NativeMethods.cs:16) and C callers bind it unchanged.
+ *
+ *  Division of labour: the graph is BUILT by the host path (the reference itself,
+ *  or any writer of the v2 `.usearch` format), serialised, and handed to this library through
+ *  `usearch_load[_buffer]` / `usearch_view[_buffer]`, which freeze it into a flat SoA layout in
+ *  HBM. From then on every `usearch_search` / `usearch_search_many` runs on the GPU. Mutating
+ *  entry points are exported so that existing bindings link, and report
+ *  "Index is frozen in GPU memory ..." through `error` (the reference's own convention for an
+ *  immutable `view`, index.hpp:2787-2788).
+ *
+ *  Error convention (usearch.h:24-28): `*error` receives a pointer to a static, NUL-terminated
+ *  message that must not be freed; it is left untouched on success. Nothing throws across the ABI.
+ *
+ *  `usearch_b200_*` symbols are additive: the batch entry the reference lacks (SURVEY.md
+ *  finding 2; python/lib.cpp:286-308 loops single-query calls on a thread pool instead), a
+ *  device-pointer variant for callers that already hold queries in HBM, and introspection.
+ */
+#ifndef USEARCH_B200_H
+#define USEARCH_B200_H
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- types: identical to usearch.h:20-110 ------------------------------------------------ */
+
+typedef void* usearch_index_t;
+typedef uint64_t usearch_key_t;
+typedef float usearch_distance_t;
+typedef char const* usearch_error_t;
+typedef usearch_distance_t (*usearch_metric_t)(void const*, void const*);
+
+typedef enum usearch_metric_kind_t { /* usearch.h:40-52 */
+    usearch_metric_unknown_k = 0,
+    usearch_metric_cos_k = 1,
+    usearch_metric_ip_k = 2,
+    usearch_metric_l2sq_k = 3,
+    usearch_metric_haversine_k = 4,
+    usearch_metric_divergence_k = 5,
+    usearch_metric_pearson_k = 6,
+    usearch_metric_jaccard_k = 7,
+    usearch_metric_hamming_k = 8,
+    usearch_metric_tanimoto_k = 9,
+    usearch_metric_sorensen_k = 10,
+} usearch_metric_kind_t;
+
+typedef enum usearch_scalar_kind_t { /* usearch.h:54-62 */
+    usearch_scalar_unknown_k = 0,
+    usearch_scalar_f32_k = 1,
+    usearch_scalar_f64_k = 2,
+    usearch_scalar_f16_k = 3,
+    usearch_scalar_i8_k = 4,
+    usearch_scalar_b1_k = 5,
+    usearch_scalar_bf16_k = 6,
+} usearch_scalar_kind_t;
+
+typedef struct usearch_init_options_t { /* usearch.h:64-110, same field order */
+    usearch_metric_kind_t metric_kind;
+    usearch_metric_t metric; /* custom host callbacks cannot run on the device: must be NULL */
+    usearch_scalar_kind_t quantization;
+    size_t dimensions;
+    size_t connectivity;
+    size_t expansion_add;
+    size_t expansion_search;
+    bool multi;
+} usearch_init_options_t;
+
+/* ---- lifecycle & introspection ----------------------------------------------------------- */
+
+char const* usearch_version(void);                                                      /* usearch.h:116 */
+usearch_index_t usearch_init(usearch_init_options_t* options, usearch_error_t* error);  /* usearch.h:124; NULL options = empty index awaiting load (c/lib.cpp:142-147) */
+void usearch_free(usearch_index_t index, usearch_error_t* error);                       /* usearch.h:131 */
+size_t usearch_memory_usage(usearch_index_t index, usearch_error_t* error);             /* usearch.h:139; bytes of HBM held */
+char const* usearch_hardware_acceleration(usearch_index_t index, usearch_error_t* error); /* usearch.h:147; "sm_100a" */
+size_t usearch_serialized_length(usearch_index_t index, usearch_error_t* error);        /* usearch.h:154 */
+
+/* ---- the hand-off: v2 `.usearch` blob → HBM (index_dense.hpp:1084-1188, index.hpp:3322-3382) */
+
+void usearch_save(usearch_index_t index, char const* path, usearch_error_t* error);     /* usearch.h:162 */
+void usearch_load(usearch_index_t index, char const* path, usearch_error_t* error);     /* usearch.h:170 */
+void usearch_view(usearch_index_t index, char const* path, usearch_error_t* error);     /* usearch.h:178; same as load: the device copy never aliases the file */
+void usearch_metadata(char const* path, usearch_init_options_t* options, usearch_error_t* error); /* usearch.h:186 */
+void usearch_save_buffer(usearch_index_t index, void* buffer, size_t length, usearch_error_t* error);        /* usearch.h:195 */
+void usearch_load_buffer(usearch_index_t index, void const* buffer, size_t length, usearch_error_t* error);  /* usearch.h:204 */
+void usearch_view_buffer(usearch_index_t index, void const* buffer, size_t length, usearch_error_t* error);  /* usearch.h:214 */
+void usearch_metadata_buffer(void const* buffer, size_t length, usearch_init_options_t* options, usearch_error_t* error); /* usearch.h:223 */
+
+size_t usearch_size(usearch_index_t index, usearch_error_t* error);          /* usearch.h:231 */
+size_t usearch_capacity(usearch_index_t index, usearch_error_t* error);      /* usearch.h:238 */
+size_t usearch_dimensions(usearch_index_t index, usearch_error_t* error);    /* usearch.h:245 */
+size_t usearch_connectivity(usearch_index_t index, usearch_error_t* error);  /* usearch.h:252 */
+void usearch_reserve(usearch_index_t index, size_t capacity, usearch_error_t* error); /* usearch.h:260; no-op on a frozen index */
+size_t usearch_expansion_add(usearch_index_t index, usearch_error_t* error);          /* usearch.h:268 */
+size_t usearch_expansion_search(usearch_index_t index, usearch_error_t* error);       /* usearch.h:276 */
+void usearch_change_expansion_add(usearch_index_t index, size_t expansion, usearch_error_t* error);    /* usearch.h:284 */
+void usearch_change_expansion_search(usearch_index_t index, size_t expansion, usearch_error_t* error); /* usearch.h:292 */
+void usearch_change_threads_add(usearch_index_t index, size_t threads, usearch_error_t* error);        /* usearch.h:300; accepted, ignored */
+void usearch_change_threads_search(usearch_index_t index, size_t threads, usearch_error_t* error);     /* usearch.h:308; accepted, ignored */
+void usearch_change_metric_kind(usearch_index_t index, usearch_metric_kind_t kind, usearch_error_t* error); /* usearch.h:316 */
+void usearch_change_metric(usearch_index_t index, usearch_metric_t metric, void* state, usearch_metric_kind_t kind, usearch_error_t* error); /* usearch.h:327; host callbacks rejected */
+
+/* ---- the hot path ------------------------------------------------------------------------ */
+
+/* usearch.h:371-374, c/lib.cpp:398-411. Returns the number of matches; ALWAYS writes `count`
+ * output slots, padding with key 0 / signalling-NaN distance (index.hpp:2707-2722). The query
+ * may be of any scalar kind; it is cast to the index's kind with the reference's rules
+ * (index_plugins.hpp:1105-1224). */
+size_t usearch_search(usearch_index_t index, void const* query_vector, usearch_scalar_kind_t query_kind, size_t count,
+                      usearch_key_t* keys, usearch_distance_t* distances, usearch_error_t* error);
+
+/* usearch.h:391-395. Host callbacks cannot run on the device: reports an error unless `filter` is NULL. */
+size_t usearch_filtered_search(usearch_index_t index, void const* query_vector, usearch_scalar_kind_t query_kind,
+                               size_t count, int (*filter)(usearch_key_t key, void* filter_state), void* filter_state,
+                               usearch_key_t* keys, usearch_distance_t* distances, usearch_error_t* error);
+
+/* NEW (additive). One call = one batch = one persistent-kernel launch. Strides are in BYTES,
+ * in the style of usearch_exact_search (usearch.h:467-474). `counts` receives the per-query
+ * number of matches. Replaces the thread-pool loop in python/lib.cpp:261-319 (`search_typed`)
+ * and cpp/bench.cpp:352-377. Buffers are HOST memory; copies are part of the call. Returns the
+ * sum of counts. */
+size_t usearch_search_many(usearch_index_t index, void const* queries, size_t queries_count, size_t queries_stride,
+                           usearch_scalar_kind_t query_kind, size_t count,              //
+                           usearch_key_t* keys, size_t keys_stride,                     //
+                           usearch_distance_t* distances, size_t distances_stride,      //
+                           size_t* counts, usearch_error_t* error);
+
+/* ---- exported so existing bindings link; a frozen index reports an error ------------------- */
+
+void usearch_add(usearch_index_t index, usearch_key_t key, void const* vector, usearch_scalar_kind_t vector_kind, usearch_error_t* error); /* usearch.h:338 */
+bool usearch_contains(usearch_index_t index, usearch_key_t key, usearch_error_t* error);   /* usearch.h:349 */
+size_t usearch_count(usearch_index_t index, usearch_key_t key, usearch_error_t* error);    /* usearch.h:358 */
+size_t usearch_get(usearch_index_t index, usearch_key_t key, size_t count, void* vector, usearch_scalar_kind_t vector_kind, usearch_error_t* error); /* usearch.h:407 */
+size_t usearch_remove(usearch_index_t index, usearch_key_t key, usearch_error_t* error);   /* usearch.h:418 */
+size_t usearch_rename(usearch_index_t index, usearch_key_t from, usearch_key_t to, usearch_error_t* error); /* usearch.h:428 */
+usearch_distance_t usearch_distance(void const* vector_first, void const* vector_second, usearch_scalar_kind_t scalar_kind,
+                                    size_t dimensions, usearch_metric_kind_t metric_kind, usearch_error_t* error); /* usearch.h:441 */
+void usearch_exact_search(void const* dataset, size_t dataset_size, size_t dataset_stride, void const* queries,
+                          size_t queries_size, size_t queries_stride, usearch_scalar_kind_t scalar_kind, size_t dimensions,
+                          usearch_metric_kind_t metric_kind, size_t count, size_t threads, usearch_key_t* keys,
+                          size_t keys_stride, usearch_distance_t* distances, size_t distances_stride,
+                          usearch_error_t* error); /* usearch.h:467 */
+void usearch_clear(usearch_index_t index, usearch_error_t* error); /* usearch.h:481 */
+
+/* ---- additive, device-resident variants ---------------------------------------------------- */
+
+/* All pointers are DEVICE pointers on the index's GPU; `queries` must already be in the index's
+ * scalar kind, rows `queries_stride` bytes apart (a multiple of 16 or equal to bytes-per-vector).
+ * `keys`/`distances` are dense [queries_count x count]; `counts`, `computed_distances` and
+ * `visited_members` (the reference's per-query counters, index.hpp:2605-2609; may be NULL) are
+ * uint32 [queries_count]. `cuda_stream` is a cudaStream_t (NULL = default stream). The call only
+ * enqueues work; it synchronises nothing unless a scratch overflow forces a retry. */
+void usearch_b200_search_many_device(usearch_index_t index, void const* queries, size_t queries_count,
+                                     size_t queries_stride, size_t count, usearch_key_t* keys,
+                                     usearch_distance_t* distances, uint32_t* counts, uint32_t* computed_distances,
+                                     uint32_t* visited_members, void* cuda_stream, usearch_error_t* error);
+
+/* Like usearch_search_many (host buffers) but also returns the reference's two counters. */
+size_t usearch_b200_search_many_stats(usearch_index_t index, void const* queries, size_t queries_count,
+                                      size_t queries_stride, usearch_scalar_kind_t query_kind, size_t count,
+                                      usearch_key_t* keys, usearch_distance_t* distances, size_t* counts,
+                                      uint64_t* computed_distances, uint64_t* visited_members, usearch_error_t* error);
+
+/* Introspection for tests / bench: CUDA device ordinal, kernel launches issued so far by this
+ * handle, duration in milliseconds of the most recent search kernel (CUDA events on its stream). */
+int usearch_b200_device(usearch_index_t index);
+uint64_t usearch_b200_kernel_launches(usearch_index_t index);
+float usearch_b200_last_kernel_ms(usearch_index_t index);
+size_t usearch_b200_bytes_per_vector(usearch_index_t index);
+size_t usearch_b200_max_level(usearch_index_t index);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* USEARCH_B200_H */

@@ -60,8 +60,9 @@ static inline float pinned_dot_f32_(float const* a, float const* b, size_t n) {
 }
 
 static inline float pinned_ip_f32(float const* a, float const* b, size_t n) {
-    /* reference: result_t(1 - double(dot))  — index_plugins.hpp:1916; dot is an f32 widened */
-    return (float)(1.0 - (double)pinned_dot_f32_(a, b, n));
+    /* index_plugins.hpp:1916 invoke_simsimd_reverse: `1 - invoke_simsimd()`, and invoke_simsimd
+     * already returned a float, so the subtraction is done in f32 */
+    return 1.0f - pinned_dot_f32_(a, b, n);
 }
 
 static inline float pinned_cos_normalize_f64(double ab, double a2, double b2) {
@@ -140,7 +141,7 @@ static inline float pinned_cos_normalize_f32(float ab, float a2, float b2) {
     static inline float pinned_ip_##name(uint16_t const* a, uint16_t const* b, size_t n) {     \
         float acc[8] = {0};                                                                    \
         for (size_t i = 0; i < n; ++i) acc[i & 7] = fmaf(conv(a[i]), conv(b[i]), acc[i & 7]);  \
-        return (float)(1.0 - pinned_reduce8_(acc));                                            \
+        return 1.0f - (float)pinned_reduce8_(acc);                                             \
     }                                                                                          \
     static inline float pinned_cos_##name(uint16_t const* a, uint16_t const* b, size_t n) {    \
         float ab[8] = {0}, a2[8] = {0}, b2[8] = {0};                                           \
@@ -162,7 +163,7 @@ PINNED_HALF_KERNELS_(bf16, pinned_bf16_to_f32)
 static inline float pinned_ip_i8(int8_t const* a, int8_t const* b, size_t n) {
     int32_t ab = 0;
     for (size_t i = 0; i < n; ++i) ab += (int32_t)a[i] * (int32_t)b[i];
-    return (float)(1.0 - (double)ab); /* dot_i8 → f64 → 1 - dot → f32 */
+    return 1.0f - (float)ab; /* dot_i8 -> f64 -> cast to f32 -> `1 - x` in f32 (index_plugins.hpp:1914-1916) */
 }
 
 static inline float pinned_l2sq_i8(int8_t const* a, int8_t const* b, size_t n) {

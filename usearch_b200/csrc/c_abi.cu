@@ -1,0 +1,338 @@
+/*
+ *  c_abi.cu — the `extern "C"` boundary declared in include/usearch_b200.h.
+ *
+ *  Each function keeps the name, arguments and error behaviour of the reference entry point it
+ *  replaces (c/lib.cpp:125-507); only the search path does work, on the GPU. No torch types, no
+ *  C++ types and no exceptions cross this boundary.
+ */
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <fcntl.h>
+#include <unistd.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "../../include/usearch_b200.h"
+#include "frozen_index.h"
+
+using namespace usearch_b200;
+
+namespace {
+
+char const* const FROZEN = "Index is frozen in GPU memory: build or modify it with the host library, then load it";
+
+uint32_t metric_to_char(usearch_metric_kind_t kind) { /* c/lib.cpp:26-40 */
+    switch (kind) {
+    case usearch_metric_ip_k: return METRIC_IP;
+    case usearch_metric_l2sq_k: return METRIC_L2SQ;
+    case usearch_metric_cos_k: return METRIC_COS;
+    case usearch_metric_haversine_k: return 'h';
+    case usearch_metric_divergence_k: return 'd';
+    case usearch_metric_pearson_k: return 'p';
+    case usearch_metric_jaccard_k: return METRIC_JACCARD;
+    case usearch_metric_hamming_k: return METRIC_HAMMING;
+    case usearch_metric_tanimoto_k: return METRIC_TANIMOTO;
+    case usearch_metric_sorensen_k: return METRIC_SORENSEN;
+    default: return 0;
+    }
+}
+usearch_metric_kind_t metric_to_c(uint32_t c) { /* c/lib.cpp:42-56 */
+    switch (c) {
+    case METRIC_IP: return usearch_metric_ip_k;
+    case METRIC_L2SQ: return usearch_metric_l2sq_k;
+    case METRIC_COS: return usearch_metric_cos_k;
+    case 'h': return usearch_metric_haversine_k;
+    case 'd': return usearch_metric_divergence_k;
+    case 'p': return usearch_metric_pearson_k;
+    case METRIC_JACCARD: return usearch_metric_jaccard_k;
+    case METRIC_HAMMING: return usearch_metric_hamming_k;
+    case METRIC_TANIMOTO: return usearch_metric_tanimoto_k;
+    case METRIC_SORENSEN: return usearch_metric_sorensen_k;
+    default: return usearch_metric_unknown_k;
+    }
+}
+uint32_t scalar_to_char(usearch_scalar_kind_t kind) { /* c/lib.cpp:57-67 */
+    switch (kind) {
+    case usearch_scalar_f32_k: return SCALAR_F32;
+    case usearch_scalar_f64_k: return SCALAR_F64;
+    case usearch_scalar_f16_k: return SCALAR_F16;
+    case usearch_scalar_bf16_k: return SCALAR_BF16;
+    case usearch_scalar_i8_k: return SCALAR_I8;
+    case usearch_scalar_b1_k: return SCALAR_B1;
+    default: return 0;
+    }
+}
+usearch_scalar_kind_t scalar_to_c(uint32_t c) { /* c/lib.cpp:69-79 */
+    switch (c) {
+    case SCALAR_F32: return usearch_scalar_f32_k;
+    case SCALAR_F64: return usearch_scalar_f64_k;
+    case SCALAR_F16: return usearch_scalar_f16_k;
+    case SCALAR_BF16: return usearch_scalar_bf16_k;
+    case SCALAR_I8: return usearch_scalar_i8_k;
+    case SCALAR_B1: return usearch_scalar_b1_k;
+    default: return usearch_scalar_unknown_k;
+    }
+}
+
+frozen_index_t* as_index(usearch_index_t h) { return reinterpret_cast<frozen_index_t*>(h); }
+
+void set_error(usearch_error_t* error, char const* message) {
+    if (error && message) *error = message;
+}
+
+/* read-only mapping of a file, handed to load_blob */
+struct mapped_file_t {
+    void* ptr = nullptr;
+    size_t length = 0;
+    int fd = -1;
+    char const* open(char const* path) {
+        fd = ::open(path, O_RDONLY);
+        if (fd < 0) return "Can't open file";
+        struct stat st;
+        if (fstat(fd, &st) != 0) return "Can't stat file";
+        length = (size_t)st.st_size;
+        ptr = mmap(nullptr, length, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (ptr == MAP_FAILED) { ptr = nullptr; return "Can't memory-map file"; }
+        return nullptr;
+    }
+    ~mapped_file_t() {
+        if (ptr) munmap(ptr, length);
+        if (fd >= 0) ::close(fd);
+    }
+};
+
+char const* metadata_from(uint8_t const* blob, size_t length, usearch_init_options_t* options) {
+    /* index_dense.hpp:253-369 metadata sniffers: skip the matrix, read the 64-byte head */
+    if (length < 8 + 64) return "File is corrupted and lacks a header";
+    uint32_t rows, cols;
+    std::memcpy(&rows, blob, 4);
+    std::memcpy(&cols, blob + 4, 4);
+    size_t offset = 8 + (size_t)rows * cols;
+    if (length < offset + 64) return "File is corrupted and lacks a header";
+    uint8_t const* p = blob + offset;
+    if (std::memcmp(p, "usearch", 7) != 0) return "Magic header mismatch - the file isn't an index";
+    uint64_t dims;
+    std::memcpy(&dims, p + 33, 8);
+    options->metric_kind = metric_to_c(p[13]);
+    options->quantization = scalar_to_c(p[14]);
+    options->dimensions = dims;
+    options->multi = p[41] != 0;
+    options->connectivity = 0;
+    options->expansion_add = 0;
+    options->expansion_search = 0;
+    options->metric = nullptr;
+    return nullptr;
+}
+
+} // namespace
+
+extern "C" {
+
+char const* usearch_version(void) { return "2.21.0+b200"; }
+
+usearch_index_t usearch_init(usearch_init_options_t* options, usearch_error_t* error) {
+    frozen_index_t* index = new (std::nothrow) frozen_index_t();
+    if (!index) {
+        set_error(error, "Out of memory!");
+        return nullptr;
+    }
+    if (char const* dev = std::getenv("USEARCH_B200_DEVICE")) index->device = std::atoi(dev);
+    else if (char const* rank = std::getenv("LOCAL_RANK")) index->device = std::atoi(rank);
+    if (!options) return index; /* c/lib.cpp:142-147: empty index awaiting `load` */
+    if (options->metric) {
+        set_error(error, "Custom host metrics cannot run on the device");
+        delete index;
+        return nullptr;
+    }
+    index->metric = metric_to_char(options->metric_kind);
+    index->scalar = scalar_to_char(options->quantization);
+    if (!index->metric || !index->scalar || !search_supported(index->metric, index->scalar)) {
+        set_error(error, "Unknown metric kind!");
+        delete index;
+        return nullptr;
+    }
+    index->dimensions = options->dimensions;
+    index->connectivity = options->connectivity ? options->connectivity : 16; /* index.hpp:1340 */
+    index->connectivity_base = index->connectivity * 2;                        /* index.hpp:1368 */
+    if (options->expansion_add) index->expansion_add = options->expansion_add;
+    if (options->expansion_search) index->expansion_search = options->expansion_search;
+    index->multi = options->multi;
+    return index;
+}
+
+void usearch_free(usearch_index_t index, usearch_error_t*) { delete as_index(index); }
+
+size_t usearch_memory_usage(usearch_index_t index, usearch_error_t*) { return as_index(index)->hbm_bytes; }
+
+char const* usearch_hardware_acceleration(usearch_index_t, usearch_error_t*) { return "sm_100a"; }
+
+size_t usearch_serialized_length(usearch_index_t index, usearch_error_t*) { return as_index(index)->serialized_length(); }
+
+void usearch_save_buffer(usearch_index_t index, void* buffer, size_t length, usearch_error_t* error) {
+    set_error(error, as_index(index)->save_blob(static_cast<uint8_t*>(buffer), length));
+}
+
+void usearch_load_buffer(usearch_index_t index, void const* buffer, size_t length, usearch_error_t* error) {
+    frozen_index_t* ix = as_index(index);
+    std::lock_guard<std::mutex> lock(ix->mutex);
+    set_error(error, ix->load_blob(static_cast<uint8_t const*>(buffer), length));
+}
+
+void usearch_view_buffer(usearch_index_t index, void const* buffer, size_t length, usearch_error_t* error) {
+    usearch_load_buffer(index, buffer, length, error);
+}
+
+void usearch_metadata_buffer(void const* buffer, size_t length, usearch_init_options_t* options, usearch_error_t* error) {
+    set_error(error, metadata_from(static_cast<uint8_t const*>(buffer), length, options));
+}
+
+void usearch_load(usearch_index_t index, char const* path, usearch_error_t* error) {
+    mapped_file_t file;
+    if (char const* e = file.open(path)) return set_error(error, e);
+    usearch_load_buffer(index, file.ptr, file.length, error);
+}
+
+void usearch_view(usearch_index_t index, char const* path, usearch_error_t* error) { usearch_load(index, path, error); }
+
+void usearch_metadata(char const* path, usearch_init_options_t* options, usearch_error_t* error) {
+    mapped_file_t file;
+    if (char const* e = file.open(path)) return set_error(error, e);
+    set_error(error, metadata_from(static_cast<uint8_t const*>(file.ptr), file.length, options));
+}
+
+void usearch_save(usearch_index_t index, char const* path, usearch_error_t* error) {
+    frozen_index_t* ix = as_index(index);
+    size_t length = ix->serialized_length();
+    int fd = ::open(path, O_RDWR | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0) return set_error(error, "Can't open file");
+    if (ftruncate(fd, (off_t)length) != 0) { ::close(fd); return set_error(error, "Can't resize file"); }
+    void* ptr = mmap(nullptr, length, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    if (ptr == MAP_FAILED) { ::close(fd); return set_error(error, "Can't memory-map file"); }
+    set_error(error, ix->save_blob(static_cast<uint8_t*>(ptr), length));
+    munmap(ptr, length);
+    ::close(fd);
+}
+
+size_t usearch_size(usearch_index_t index, usearch_error_t*) { return as_index(index)->size - as_index(index)->count_deleted; }
+size_t usearch_capacity(usearch_index_t index, usearch_error_t*) { return as_index(index)->size; }
+size_t usearch_dimensions(usearch_index_t index, usearch_error_t*) { return as_index(index)->dimensions; }
+size_t usearch_connectivity(usearch_index_t index, usearch_error_t*) { return as_index(index)->connectivity; }
+void usearch_reserve(usearch_index_t, size_t, usearch_error_t*) {}
+size_t usearch_expansion_add(usearch_index_t index, usearch_error_t*) { return as_index(index)->expansion_add; }
+size_t usearch_expansion_search(usearch_index_t index, usearch_error_t*) { return as_index(index)->expansion_search; }
+void usearch_change_expansion_add(usearch_index_t index, size_t expansion, usearch_error_t*) { as_index(index)->expansion_add = expansion; }
+void usearch_change_expansion_search(usearch_index_t index, size_t expansion, usearch_error_t*) { as_index(index)->expansion_search = expansion; }
+void usearch_change_threads_add(usearch_index_t, size_t, usearch_error_t*) {}
+void usearch_change_threads_search(usearch_index_t, size_t, usearch_error_t*) {}
+
+void usearch_change_metric_kind(usearch_index_t index, usearch_metric_kind_t kind, usearch_error_t* error) {
+    frozen_index_t* ix = as_index(index);
+    uint32_t m = metric_to_char(kind);
+    if (!m || !search_supported(m, ix->scalar)) return set_error(error, "Unknown metric kind!");
+    std::lock_guard<std::mutex> lock(ix->mutex);
+    ix->metric = m;
+    ix->d.metric = m;
+}
+
+void usearch_change_metric(usearch_index_t, usearch_metric_t, void*, usearch_metric_kind_t, usearch_error_t* error) {
+    set_error(error, "Custom host metrics cannot run on the device");
+}
+
+size_t usearch_search(usearch_index_t index, void const* query, usearch_scalar_kind_t query_kind, size_t count,
+                      usearch_key_t* keys, usearch_distance_t* distances, usearch_error_t* error) {
+    frozen_index_t* ix = as_index(index);
+    uint32_t qs = scalar_to_char(query_kind);
+    if (!qs) { set_error(error, "Unknown scalar kind!"); return 0; }
+    size_t total = 0;
+    size_t qbytes = (ix->dimensions * bits_per_scalar(qs) + 7) / 8;
+    if (char const* e = ix->search_host(query, 1, qbytes, qs, count, keys, count * 8, distances, count * 4, nullptr,
+                                        nullptr, nullptr, &total)) {
+        set_error(error, e);
+        return 0;
+    }
+    return total;
+}
+
+size_t usearch_filtered_search(usearch_index_t index, void const* query, usearch_scalar_kind_t query_kind, size_t count,
+                               int (*filter)(usearch_key_t, void*), void*, usearch_key_t* keys,
+                               usearch_distance_t* distances, usearch_error_t* error) {
+    if (filter) {
+        set_error(error, "Host predicates cannot run on the device");
+        return 0;
+    }
+    return usearch_search(index, query, query_kind, count, keys, distances, error);
+}
+
+size_t usearch_search_many(usearch_index_t index, void const* queries, size_t queries_count, size_t queries_stride,
+                           usearch_scalar_kind_t query_kind, size_t count, usearch_key_t* keys, size_t keys_stride,
+                           usearch_distance_t* distances, size_t distances_stride, size_t* counts, usearch_error_t* error) {
+    frozen_index_t* ix = as_index(index);
+    uint32_t qs = scalar_to_char(query_kind);
+    if (!qs) { set_error(error, "Unknown scalar kind!"); return 0; }
+    size_t total = 0;
+    if (char const* e = ix->search_host(queries, queries_count, queries_stride, qs, count, keys, keys_stride, distances,
+                                        distances_stride, counts, nullptr, nullptr, &total)) {
+        set_error(error, e);
+        return 0;
+    }
+    return total;
+}
+
+size_t usearch_b200_search_many_stats(usearch_index_t index, void const* queries, size_t queries_count, size_t queries_stride,
+                                      usearch_scalar_kind_t query_kind, size_t count, usearch_key_t* keys,
+                                      usearch_distance_t* distances, size_t* counts, uint64_t* computed_distances,
+                                      uint64_t* visited_members, usearch_error_t* error) {
+    frozen_index_t* ix = as_index(index);
+    uint32_t qs = scalar_to_char(query_kind);
+    if (!qs) { set_error(error, "Unknown scalar kind!"); return 0; }
+    size_t total = 0;
+    if (char const* e = ix->search_host(queries, queries_count, queries_stride, qs, count, keys, count * 8, distances,
+                                        count * 4, counts, computed_distances, visited_members, &total)) {
+        set_error(error, e);
+        return 0;
+    }
+    return total;
+}
+
+void usearch_b200_search_many_device(usearch_index_t index, void const* queries, size_t queries_count, size_t queries_stride,
+                                     size_t count, usearch_key_t* keys, usearch_distance_t* distances, uint32_t* counts,
+                                     uint32_t* computed_distances, uint32_t* visited_members, void* cuda_stream,
+                                     usearch_error_t* error) {
+    frozen_index_t* ix = as_index(index);
+    if (char const* e = ix->ensure_context()) return set_error(error, e);
+    std::lock_guard<std::mutex> lock(ix->mutex);
+    cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ix->stream;
+    set_error(error, ix->search_device(queries, queries_count, queries_stride, count, keys, distances, counts,
+                                       computed_distances, visited_members, s));
+}
+
+void usearch_add(usearch_index_t, usearch_key_t, void const*, usearch_scalar_kind_t, usearch_error_t* error) { set_error(error, FROZEN); }
+bool usearch_contains(usearch_index_t, usearch_key_t, usearch_error_t* error) { set_error(error, FROZEN); return false; }
+size_t usearch_count(usearch_index_t, usearch_key_t, usearch_error_t* error) { set_error(error, FROZEN); return 0; }
+size_t usearch_get(usearch_index_t, usearch_key_t, size_t, void*, usearch_scalar_kind_t, usearch_error_t* error) { set_error(error, FROZEN); return 0; }
+size_t usearch_remove(usearch_index_t, usearch_key_t, usearch_error_t* error) { set_error(error, FROZEN); return 0; }
+size_t usearch_rename(usearch_index_t, usearch_key_t, usearch_key_t, usearch_error_t* error) { set_error(error, FROZEN); return 0; }
+usearch_distance_t usearch_distance(void const*, void const*, usearch_scalar_kind_t, size_t, usearch_metric_kind_t, usearch_error_t* error) {
+    set_error(error, "Scalar distances are not offloaded: call the host library");
+    return 0;
+}
+void usearch_exact_search(void const*, size_t, size_t, void const*, size_t, size_t, usearch_scalar_kind_t, size_t,
+                          usearch_metric_kind_t, size_t, size_t, usearch_key_t*, size_t, usearch_distance_t*, size_t,
+                          usearch_error_t* error) {
+    set_error(error, "Exact search is not offloaded yet: call the host library");
+}
+void usearch_clear(usearch_index_t index, usearch_error_t*) {
+    frozen_index_t* ix = as_index(index);
+    std::lock_guard<std::mutex> lock(ix->mutex);
+    ix->release_device();
+}
+
+int usearch_b200_device(usearch_index_t index) { return as_index(index)->device; }
+uint64_t usearch_b200_kernel_launches(usearch_index_t index) { return as_index(index)->kernel_launches; }
+float usearch_b200_last_kernel_ms(usearch_index_t index) { return as_index(index)->last_kernel_ms; }
+size_t usearch_b200_bytes_per_vector(usearch_index_t index) { return as_index(index)->d.bytes_per_vector; }
+size_t usearch_b200_max_level(usearch_index_t index) { return (size_t)as_index(index)->d.max_level; }
+
+} // extern "C"

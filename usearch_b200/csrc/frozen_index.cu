@@ -1,0 +1,639 @@
+/*
+ *  frozen_index.cu — host side of the GPU search backend: parse the reference's v2 serialisation,
+ *  lay the graph out as flat arrays in HBM, plan launches, run batches, retry scratch overflows.
+ *
+ *  Reference behaviour mirrored here (file:line under /root/reference/include/usearch):
+ *    index_dense.hpp:1084-1188  load_from_stream: [u32 rows, u32 cols][matrix][64-byte head][graph]
+ *    index_dense.hpp:42-79      index_dense_head_t field order
+ *    index.hpp:3322-3382        graph: 40-byte header | int16 levels | node tapes
+ *    index.hpp:2116-2195        node tape: key u64 | level i16 | {u32 n, slot[M0]} | level x {u32 n, slot[M]}
+ *    index.hpp:3016-3075        expansion = max(config.expansion or 64, wanted)
+ *    index_plugins.hpp:1105-1224 query casts
+ */
+#include "frozen_index.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace usearch_b200 {
+
+namespace {
+
+uint64_t rd_u64(uint8_t const* p) { uint64_t v; std::memcpy(&v, p, 8); return v; }
+uint32_t rd_u32(uint8_t const* p) { uint32_t v; std::memcpy(&v, p, 4); return v; }
+int16_t rd_i16(uint8_t const* p) { int16_t v; std::memcpy(&v, p, 2); return v; }
+uint32_t ceil2(uint64_t v) { uint64_t r = 1; while (r < v) r <<= 1; return (uint32_t)std::min<uint64_t>(r, 1ull << 31); }
+uint32_t round_up(uint32_t v, uint32_t m) { return (v + m - 1) / m * m; }
+
+char const* cuda_error(cudaError_t e) {
+    if (e == cudaSuccess) return nullptr;
+    cudaGetLastError();
+    if (e == cudaErrorMemoryAllocation) return "Out of GPU memory!";
+    static thread_local char message[160];
+    std::snprintf(message, sizeof(message), "CUDA failure: %s", cudaGetErrorString(e));
+    return message;
+}
+
+#define CU(call)                                             \
+    do {                                                     \
+        if (char const* err_ = cuda_error((call))) return err_; \
+    } while (0)
+
+} // namespace
+
+size_t bits_per_scalar(uint32_t s) { /* index_plugins.hpp:237-257 */
+    switch (s) {
+    case SCALAR_B1: return 1;
+    case SCALAR_I8: return 8;
+    case SCALAR_F16: case SCALAR_BF16: return 16;
+    case SCALAR_F32: return 32;
+    case SCALAR_F64: return 64;
+    default: return 0;
+    }
+}
+
+frozen_index_t::~frozen_index_t() {
+    release_device();
+    if (stream) cudaStreamDestroy(stream);
+    if (ev_begin) cudaEventDestroy(ev_begin);
+    if (ev_end) cudaEventDestroy(ev_end);
+    visited.release(); work_counter.release(); status.release(); counts.release(); computed.release();
+    cycles.release(); retry_list.release(); heap_spill.release(); queries.release(); out_keys.release();
+    out_dists.release(); h_queries.release(); h_keys.release(); h_dists.release(); h_counts.release();
+    h_computed.release(); h_cycles.release(); h_status.release();
+}
+
+void frozen_index_t::release_device() {
+    for (void*& p : dev_allocs) {
+        if (p) cudaFree(p);
+        p = nullptr;
+    }
+    d = device_index_t{};
+    hbm_bytes = 0;
+    loaded = false;
+    size = 0;
+    count_deleted = 0;
+    levels.clear();
+}
+
+char const* frozen_index_t::ensure_context() {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return "No CUDA device: the B200 search backend has no CPU fallback";
+    }
+    CU(cudaSetDevice(device));
+    if (!stream) {
+        CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        CU(cudaEventCreate(&ev_begin));
+        CU(cudaEventCreate(&ev_end));
+        CU(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
+    }
+    return nullptr;
+}
+
+char const* frozen_index_t::counts_reserve_all(size_t nq) {
+    if (char const* e = counts.reserve(nq)) return e;
+    if (char const* e = computed.reserve(nq)) return e;
+    if (char const* e = cycles.reserve(nq)) return e;
+    if (char const* e = h_counts.reserve(nq)) return e;
+    if (char const* e = h_computed.reserve(nq)) return e;
+    if (char const* e = h_cycles.reserve(nq)) return e;
+    return nullptr;
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/*  v2 blob -> HBM                                                                                */
+/* ---------------------------------------------------------------------------------------------- */
+
+char const* frozen_index_t::load_blob(uint8_t const* blob, size_t length) {
+    if (char const* e = ensure_context()) return e;
+    release_device();
+
+    uint8_t const* p = blob;
+    uint8_t const* const end = blob + length;
+    if (length < 8 + 64 + 40) return "File is corrupted and lacks matrix dimensions";
+    uint64_t const rows = rd_u32(p), cols = rd_u32(p + 4);
+    p += 8;
+    if ((uint64_t)(end - p) < rows * cols + 64 + 40) return "File is corrupted and lacks a header";
+    uint8_t const* const matrix = p;
+    p += rows * cols;
+    if (std::memcmp(p, "usearch", 7) != 0) return "Magic header mismatch - the file isn't an index";
+    uint16_t version_major;
+    std::memcpy(&version_major, p + 7, 2);
+    if (version_major != 2) return "File format may be different, please rebuild";
+    uint32_t const head_metric = p[13], head_scalar = p[14], head_key = p[15], head_slot = p[16];
+    if (head_key != 14 /* u64_k */) return "Key type doesn't match, consider rebuilding";
+    if (head_slot != 15 /* u32_k */) return "Slot type doesn't match, consider rebuilding";
+    uint64_t const count_present = rd_u64(p + 17), deleted = rd_u64(p + 25), dims = rd_u64(p + 33);
+    bool const head_multi = p[41] != 0;
+    p += 64;
+    (void)count_present;
+    if (!search_supported(head_metric, head_scalar))
+        return "This metric / scalar kind has no sm_100a kernel and the backend has no CPU fallback";
+    size_t const bpv = (dims * bits_per_scalar(head_scalar) + 7) / 8;
+    if (rows && cols != bpv) return "Matrix columns do not match bytes per vector";
+
+    uint64_t const n = rd_u64(p), m = rd_u64(p + 8), m0 = rd_u64(p + 16), max_level = rd_u64(p + 24), entry = rd_u64(p + 32);
+    p += 40;
+    if (n != rows) return "Index size and the number of vectors doesn't match";
+    if (n >= 0xFFFFFFFFull) return "Too many entries for 32-bit slots";
+    if (n && (m < 2 || m0 < 2)) return "Connectivity is too low";
+    if ((uint64_t)(end - p) < n * 2) return "File is corrupted and can't fit all the levels";
+    uint8_t const* const levels_bytes = p;
+    p += n * 2;
+
+    metric = head_metric;
+    scalar = head_scalar;
+    dimensions = dims;
+    connectivity = m;
+    connectivity_base = m0;
+    multi = head_multi;
+    size = n;
+    count_deleted = deleted;
+
+    device_index_t ix;
+    ix.n = (uint32_t)n;
+    ix.m = (uint32_t)m;
+    ix.m0 = (uint32_t)m0;
+    ix.m_stride = round_up((uint32_t)m, 4);
+    ix.m0_stride = round_up((uint32_t)m0, 4);
+    ix.entry_slot = (uint32_t)entry;
+    ix.max_level = (int32_t)max_level;
+    ix.dims = (uint32_t)dims;
+    ix.bytes_per_vector = (uint32_t)bpv;
+    ix.vec_stride = round_up((uint32_t)bpv, 16);
+    ix.chunks16 = (uint32_t)(ix.vec_stride / 16);
+    ix.metric = metric;
+    ix.scalar = scalar;
+    if (n == 0) {
+        d = ix;
+        loaded = true;
+        return nullptr;
+    }
+
+    /* pass 1: levels, upper row offsets, tape offsets */
+    levels.resize(n);
+    std::vector<uint32_t> upper_base(n);
+    uint64_t upper_rows = 0;
+    size_t const nb = m * 4 + 4, nb0 = m0 * 4 + 4;
+    {
+        uint8_t const* q = p;
+        for (uint64_t i = 0; i < n; ++i) {
+            int16_t level = rd_i16(levels_bytes + 2 * i);
+            if (level < 0) return "File is corrupted: negative level";
+            levels[i] = level;
+            upper_base[i] = level ? (uint32_t)upper_rows : EMPTY_SLOT;
+            upper_rows += (uint64_t)level;
+            size_t node_bytes = 10 + nb0 + nb * (size_t)level;
+            if ((size_t)(end - q) < node_bytes) return "File is corrupted and can't fit all the nodes";
+            q += node_bytes;
+        }
+        if (upper_rows >= 0xFFFFFFFFull) return "Too many upper-level rows";
+    }
+
+    /* device allocations */
+    uint8_t* d_vectors = nullptr;
+    uint64_t* d_keys = nullptr;
+    uint32_t *d_nbr0 = nullptr, *d_upper_base = nullptr, *d_upper = nullptr, *d_deleted = nullptr;
+    size_t const bytes_vectors = (size_t)n * ix.vec_stride, bytes_keys = (size_t)n * 8,
+                 bytes_nbr0 = (size_t)n * ix.m0_stride * 4, bytes_ub = (size_t)n * 4,
+                 bytes_upper = std::max<size_t>(upper_rows, 1) * ix.m_stride * 4, bytes_deleted = ((size_t)n + 31) / 32 * 4;
+    CU(cudaMalloc(&d_vectors, bytes_vectors)); dev_allocs[0] = d_vectors;
+    CU(cudaMalloc(&d_keys, bytes_keys)); dev_allocs[1] = d_keys;
+    CU(cudaMalloc(&d_nbr0, bytes_nbr0)); dev_allocs[2] = d_nbr0;
+    CU(cudaMalloc(&d_upper_base, bytes_ub)); dev_allocs[3] = d_upper_base;
+    CU(cudaMalloc(&d_upper, bytes_upper)); dev_allocs[4] = d_upper;
+    hbm_bytes = bytes_vectors + bytes_keys + bytes_nbr0 + bytes_ub + bytes_upper;
+
+    /* vectors: slot-major matrix, rows padded to 16 bytes */
+    if (ix.vec_stride == bpv) {
+        CU(cudaMemcpy(d_vectors, matrix, bytes_vectors, cudaMemcpyHostToDevice));
+    } else {
+        CU(cudaMemset(d_vectors, 0, bytes_vectors));
+        CU(cudaMemcpy2D(d_vectors, ix.vec_stride, matrix, bpv, bpv, n, cudaMemcpyHostToDevice));
+    }
+
+    /* pass 2: node tapes -> keys, nbr0 rows, upper rows; converted and uploaded in chunks */
+    size_t const chunk_nodes = 1u << 18;
+    std::vector<uint64_t> h_keys(std::min<size_t>(n, chunk_nodes));
+    std::vector<uint32_t> h_nbr0(std::min<size_t>(n, chunk_nodes) * ix.m0_stride);
+    std::vector<uint32_t> h_upper;
+    std::vector<uint32_t> h_deleted(((size_t)n + 31) / 32, 0u);
+    bool any_deleted = false;
+    uint8_t const* q = p;
+    for (uint64_t begin = 0; begin < n; begin += chunk_nodes) {
+        uint64_t const stop = std::min<uint64_t>(n, begin + chunk_nodes);
+        uint64_t const first_upper_row = [&] { for (uint64_t i = begin; i < stop; ++i) if (levels[i]) return (uint64_t)upper_base[i]; return upper_rows; }();
+        uint64_t chunk_upper_rows = 0;
+        for (uint64_t i = begin; i < stop; ++i) chunk_upper_rows += (uint64_t)levels[i];
+        h_upper.assign(chunk_upper_rows * ix.m_stride, EMPTY_SLOT);
+        std::fill(h_nbr0.begin(), h_nbr0.begin() + (stop - begin) * ix.m0_stride, EMPTY_SLOT);
+        uint64_t row = 0;
+        for (uint64_t i = begin; i < stop; ++i) {
+            uint64_t key = rd_u64(q);
+            h_keys[i - begin] = key;
+            if (key == free_key) { h_deleted[i >> 5] |= 1u << (i & 31); any_deleted = true; }
+            uint8_t const* list = q + 10;
+            uint32_t c0 = std::min<uint32_t>(rd_u32(list), (uint32_t)m0);
+            uint32_t* dst0 = h_nbr0.data() + (i - begin) * ix.m0_stride;
+            for (uint32_t j = 0; j < c0; ++j) {
+                uint32_t s = rd_u32(list + 4 + 4 * j);
+                if (s >= n) return "File is corrupted: neighbour slot out of range";
+                dst0[j] = s;
+            }
+            list += nb0;
+            for (int16_t l = 0; l < levels[i]; ++l, ++row, list += nb) {
+                uint32_t c = std::min<uint32_t>(rd_u32(list), (uint32_t)m);
+                uint32_t* dst = h_upper.data() + row * ix.m_stride;
+                for (uint32_t j = 0; j < c; ++j) {
+                    uint32_t s = rd_u32(list + 4 + 4 * j);
+                    if (s >= n) return "File is corrupted: neighbour slot out of range";
+                    dst[j] = s;
+                }
+            }
+            q = list;
+        }
+        CU(cudaMemcpy(d_keys + begin, h_keys.data(), (stop - begin) * 8, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(d_nbr0 + begin * ix.m0_stride, h_nbr0.data(), (stop - begin) * ix.m0_stride * 4, cudaMemcpyHostToDevice));
+        if (chunk_upper_rows)
+            CU(cudaMemcpy(d_upper + first_upper_row * ix.m_stride, h_upper.data(), chunk_upper_rows * ix.m_stride * 4,
+                          cudaMemcpyHostToDevice));
+    }
+    CU(cudaMemcpy(d_upper_base, upper_base.data(), bytes_ub, cudaMemcpyHostToDevice));
+    if (any_deleted) {
+        CU(cudaMalloc(&d_deleted, bytes_deleted)); dev_allocs[5] = d_deleted;
+        CU(cudaMemcpy(d_deleted, h_deleted.data(), bytes_deleted, cudaMemcpyHostToDevice));
+        hbm_bytes += bytes_deleted;
+    }
+    if (entry >= n) return "File is corrupted: entry slot out of range";
+
+    ix.vectors = d_vectors;
+    ix.keys = d_keys;
+    ix.nbr0 = d_nbr0;
+    ix.upper_base = d_upper_base;
+    ix.upper = d_upper;
+    ix.deleted_bits = d_deleted;
+    d = ix;
+    loaded = true;
+    return nullptr;
+}
+
+size_t frozen_index_t::serialized_length() const {
+    size_t const nb = connectivity * 4 + 4, nb0 = connectivity_base * 4 + 4;
+    size_t total = 8 + size * d.bytes_per_vector + 64 + 40 + size * 2;
+    for (size_t i = 0; i < size; ++i) total += 10 + nb0 + nb * (size_t)levels[i];
+    return total;
+}
+
+/* Re-serialise the frozen index into the reference's v2 format (index_dense.hpp:994-1062,
+ * index.hpp:3276-3317) by downloading the SoA arrays. */
+char const* frozen_index_t::save_blob(uint8_t* out, size_t length) const {
+    if (length < serialized_length()) return "Failed to serialize into stream";
+    CU(cudaSetDevice(device));
+    size_t const n = size, bpv = d.bytes_per_vector;
+    uint8_t* p = out;
+    uint32_t dims32[2] = {(uint32_t)n, (uint32_t)bpv};
+    std::memcpy(p, dims32, 8);
+    p += 8;
+    if (n) {
+        if (d.vec_stride == bpv) CU(cudaMemcpy(p, d.vectors, n * bpv, cudaMemcpyDeviceToHost));
+        else CU(cudaMemcpy2D(p, bpv, d.vectors, d.vec_stride, bpv, n, cudaMemcpyDeviceToHost));
+    }
+    p += n * bpv;
+    std::memset(p, 0, 64);
+    std::memcpy(p, "usearch", 7);
+    uint16_t version[3] = {2, 21, 0};
+    std::memcpy(p + 7, version, 6);
+    p[13] = (uint8_t)metric;
+    p[14] = (uint8_t)scalar;
+    p[15] = 14; /* u64 keys */
+    p[16] = 15; /* u32 slots */
+    uint64_t present = n - count_deleted, deleted = count_deleted, dims = dimensions;
+    std::memcpy(p + 17, &present, 8);
+    std::memcpy(p + 25, &deleted, 8);
+    std::memcpy(p + 33, &dims, 8);
+    p[41] = multi ? 1 : 0;
+    p += 64;
+    uint64_t header[5] = {n, connectivity, connectivity_base, (uint64_t)d.max_level, d.entry_slot};
+    std::memcpy(p, header, 40);
+    p += 40;
+    if (!n) return nullptr;
+    std::memcpy(p, levels.data(), n * 2);
+    p += n * 2;
+    std::vector<uint64_t> h_keys(n);
+    std::vector<uint32_t> h_nbr0((size_t)n * d.m0_stride), h_ub(n);
+    size_t upper_rows = 0;
+    for (size_t i = 0; i < n; ++i) upper_rows += (size_t)levels[i];
+    std::vector<uint32_t> h_upper(std::max<size_t>(upper_rows, 1) * d.m_stride);
+    CU(cudaMemcpy(h_keys.data(), d.keys, n * 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(h_nbr0.data(), d.nbr0, h_nbr0.size() * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(h_ub.data(), d.upper_base, n * 4, cudaMemcpyDeviceToHost));
+    if (upper_rows) CU(cudaMemcpy(h_upper.data(), d.upper, upper_rows * d.m_stride * 4, cudaMemcpyDeviceToHost));
+    size_t const nb = connectivity * 4 + 4, nb0 = connectivity_base * 4 + 4;
+    auto write_list = [&](uint32_t const* row, uint32_t cap, size_t bytes) {
+        std::memset(p, 0, bytes);
+        uint32_t c = 0;
+        while (c < cap && row[c] != EMPTY_SLOT) ++c;
+        std::memcpy(p, &c, 4);
+        std::memcpy(p + 4, row, (size_t)c * 4);
+        p += bytes;
+    };
+    for (size_t i = 0; i < n; ++i) {
+        std::memcpy(p, &h_keys[i], 8);
+        std::memcpy(p + 8, &levels[i], 2);
+        p += 10;
+        write_list(h_nbr0.data() + i * d.m0_stride, d.m0, nb0);
+        for (int16_t l = 0; l < levels[i]; ++l) write_list(h_upper.data() + ((size_t)h_ub[i] + l) * d.m_stride, d.m, nb);
+    }
+    return nullptr;
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/*  launch planning                                                                               */
+/* ---------------------------------------------------------------------------------------------- */
+
+char const* frozen_index_t::plan(uint32_t k, uint32_t visited_cap_override, launch_plan_t& pl) const {
+    uint32_t ef = (uint32_t)(expansion_search ? expansion_search : 64); /* index.hpp:3029-3030 */
+    ef = std::max(ef, k);                                               /* index.hpp:3052 */
+    pl.ef = ef;
+    uint32_t const list_cap = round_up(std::max(d.m0, d.m), 32);
+    uint32_t off = 0;
+    off += d.chunks16 * 16;          /* query */
+    pl.off_top_d = off; off += round_up(ef * 4, 16);
+    pl.off_top_s = off; off += round_up(ef * 4, 16);
+    pl.off_cand_s = off; off += list_cap * 4;
+    pl.off_cand_d = off; off += list_cap * 4;
+    pl.off_heap = off;
+    uint32_t const fixed = off;
+    size_t const smem_sm = 227 * 1024;
+    int const wpb = search_warps_per_block();
+    /* aim for 24 resident warps per SM; whatever shared memory is left per warp holds the heap head */
+    uint32_t const target_warps = 24;
+    uint32_t budget = (uint32_t)(smem_sm / target_warps) & ~15u;
+    uint32_t heap_bytes = budget > fixed + 64 * 8 ? budget - fixed : 64 * 8;
+    heap_bytes = std::min<uint32_t>(heap_bytes, 4096 * 8);
+    pl.heap_smem_cap = heap_bytes / 8;
+    pl.smem_per_warp = round_up(fixed + pl.heap_smem_cap * 8, 16);
+    pl.smem_per_block = (size_t)pl.smem_per_warp * wpb;
+    if (pl.smem_per_block > smem_sm) return "Expansion or dimensionality too large for on-chip state";
+
+    uint64_t want = visited_cap_override ? visited_cap_override : (uint64_t)2 * ef * d.m0;
+    want = std::max<uint64_t>(want, 2048);
+    uint64_t const enough = (uint64_t)2 * ((uint64_t)d.n + d.m0 + 1); /* can never overflow beyond this */
+    pl.visited_cap = ceil2(std::min<uint64_t>(want, enough));
+    pl.visited_cap = std::max<uint32_t>(pl.visited_cap, 64);
+    /* pushes <= visited entries <= cap/2, so this spill can not overflow before `visits` does */
+    pl.heap_spill_cap = pl.visited_cap / 2;
+
+    int per_sm = 0;
+    CU(search_occupancy(d, &per_sm, pl.smem_per_block));
+    if (per_sm < 1) return "Kernel does not fit on an SM";
+    pl.blocks = per_sm * sm_count;
+    return nullptr;
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/*  batched search on device buffers                                                              */
+/* ---------------------------------------------------------------------------------------------- */
+
+char const* frozen_index_t::search_device(void const* d_queries, size_t nq, size_t stride, size_t k, uint64_t* d_keys,
+                                          float* d_dists, uint32_t* d_counts, uint32_t* d_computed, uint32_t* d_cycles,
+                                          cudaStream_t s) {
+    if (!loaded) return "Index is empty: load a serialized index first";
+    if (nq == 0 || k == 0) return nullptr;
+    if (nq > 0x7FFFFFFFull) return "Too many queries in one batch";
+    CU(cudaSetDevice(device));
+    launch_plan_t pl;
+    if (char const* e = plan((uint32_t)k, 0, pl)) return e;
+    /* a small batch does not need the whole grid */
+    int const wpb = search_warps_per_block();
+    int blocks = (int)std::min<size_t>((size_t)pl.blocks, (nq + wpb - 1) / wpb);
+    size_t warps = (size_t)blocks * wpb;
+
+    if (char const* e = work_counter.reserve(2)) return e;
+    if (char const* e = status.reserve(nq)) return e;
+    if (char const* e = h_status.reserve(nq)) return e;
+    if (char const* e = visited.reserve(warps * pl.visited_cap)) return e;
+    if (char const* e = heap_spill.reserve(warps * pl.heap_spill_cap)) return e;
+
+    search_args_t a;
+    a.queries = static_cast<uint8_t const*>(d_queries);
+    a.query_stride = stride;
+    a.nq = (uint32_t)nq;
+    a.k = (uint32_t)k;
+    a.ef = pl.ef;
+    a.out_keys = d_keys;
+    a.out_dists = d_dists;
+    a.out_counts = d_counts;
+    a.out_computed = d_computed;
+    a.out_visited = d_cycles;
+    a.status = status.ptr;
+    a.work_counter = work_counter.ptr;
+    a.visited = visited.ptr;
+    a.visited_cap = pl.visited_cap;
+    a.heap_spill = heap_spill.ptr;
+    a.heap_spill_cap = pl.heap_spill_cap;
+    a.heap_smem_cap = pl.heap_smem_cap;
+    a.smem_per_warp = pl.smem_per_warp;
+    a.off_top_d = pl.off_top_d; a.off_top_s = pl.off_top_s; a.off_cand_s = pl.off_cand_s;
+    a.off_cand_d = pl.off_cand_d; a.off_heap = pl.off_heap;
+
+    CU(cudaMemsetAsync(work_counter.ptr, 0, 8, s));
+    CU(cudaEventRecord(ev_begin, s));
+    CU(search_launch(d, a, blocks, pl.smem_per_block, s));
+    CU(cudaEventRecord(ev_end, s));
+    kernel_launches += 1;
+    CU(cudaMemcpyAsync(h_status.ptr, status.ptr, nq * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    CU(cudaEventElapsedTime(&last_kernel_ms, ev_begin, ev_end));
+
+    /* scratch overflow: rerun just those queries with 8x larger tables until they fit */
+    std::vector<uint32_t> failed;
+    for (size_t i = 0; i < nq; ++i)
+        if (h_status.ptr[i] != STATUS_OK) failed.push_back((uint32_t)i);
+    uint32_t cap = pl.visited_cap;
+    uint64_t const enough = (uint64_t)2 * ((uint64_t)d.n + d.m0 + 1);
+    while (!failed.empty()) {
+        if (cap >= enough) return "Search scratch overflow that a full-size table could not fix";
+        launch_plan_t rp;
+        if (char const* e = plan((uint32_t)k, (uint32_t)std::min<uint64_t>((uint64_t)cap * 8, 1ull << 31), rp)) return e;
+        cap = rp.visited_cap;
+        size_t const bytes_per_warp = (size_t)rp.visited_cap * 4 + (size_t)rp.heap_spill_cap * 8;
+        size_t max_warps = std::max<size_t>(wpb, ((size_t)2 << 30) / bytes_per_warp / wpb * wpb);
+        int rblocks = (int)std::min<size_t>({(size_t)rp.blocks, (failed.size() + wpb - 1) / wpb, max_warps / wpb});
+        rblocks = std::max(rblocks, 1);
+        size_t rwarps = (size_t)rblocks * wpb;
+        if (char const* e = visited.reserve(rwarps * rp.visited_cap)) return e;
+        if (char const* e = heap_spill.reserve(rwarps * rp.heap_spill_cap)) return e;
+        if (char const* e = retry_list.reserve(failed.size())) return e;
+        CU(cudaMemcpyAsync(retry_list.ptr, failed.data(), failed.size() * 4, cudaMemcpyHostToDevice, s));
+        search_args_t r = a;
+        r.nq = (uint32_t)failed.size();
+        r.query_list = retry_list.ptr;
+        r.visited = visited.ptr;
+        r.visited_cap = rp.visited_cap;
+        r.heap_spill = heap_spill.ptr;
+        r.heap_spill_cap = rp.heap_spill_cap;
+        CU(cudaMemsetAsync(work_counter.ptr, 0, 8, s));
+        CU(search_launch(d, r, rblocks, rp.smem_per_block, s));
+        kernel_launches += 1;
+        CU(cudaMemcpyAsync(h_status.ptr, status.ptr, nq * 4, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        std::vector<uint32_t> still;
+        for (uint32_t qi : failed)
+            if (h_status.ptr[qi] != STATUS_OK) still.push_back(qi);
+        failed.swap(still);
+    }
+    return nullptr;
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/*  host-side casts                                                                               */
+/* ---------------------------------------------------------------------------------------------- */
+
+namespace {
+
+uint16_t f32_to_f16_rn(float f) {
+    uint32_t x;
+    std::memcpy(&x, &f, 4);
+    uint32_t sign = (x >> 16) & 0x8000u;
+    uint32_t mant = x & 0x7FFFFFu;
+    int32_t exp = (int32_t)((x >> 23) & 0xFF);
+    if (exp == 255) return (uint16_t)(sign | 0x7C00u | (mant ? 0x200u | (mant >> 13) : 0));
+    exp = exp - 127 + 15;
+    if (exp >= 31) return (uint16_t)(sign | 0x7C00u);
+    if (exp <= 0) {
+        if (exp < -10) return (uint16_t)sign;
+        mant |= 0x800000u;
+        uint32_t shift = (uint32_t)(14 - exp);
+        uint32_t half = mant >> shift;
+        uint32_t rem = mant & ((1u << shift) - 1), mid = 1u << (shift - 1);
+        if (rem > mid || (rem == mid && (half & 1))) ++half;
+        return (uint16_t)(sign | half);
+    }
+    uint32_t half = ((uint32_t)exp << 10) | (mant >> 13);
+    uint32_t rem = mant & 0x1FFFu;
+    if (rem > 0x1000u || (rem == 0x1000u && (half & 1))) ++half;
+    return (uint16_t)(sign | half);
+}
+
+uint16_t f32_to_bf16_rn(float f) {
+    uint32_t x;
+    std::memcpy(&x, &f, 4);
+    if ((x & 0x7FFFFFFFu) > 0x7F800000u) return (uint16_t)((x >> 16) | 0x40u);
+    x += 0x7FFFu + ((x >> 16) & 1u);
+    return (uint16_t)(x >> 16);
+}
+
+} // namespace
+
+char const* cast_queries(uint32_t from, uint32_t to, size_t dims, uint8_t const* src, size_t src_stride, size_t nq,
+                         uint8_t* dst, size_t dst_stride) {
+    size_t const to_bytes = (dims * bits_per_scalar(to) + 7) / 8;
+    if (from == to) {
+        for (size_t i = 0; i < nq; ++i) std::memcpy(dst + i * dst_stride, src + i * src_stride, to_bytes);
+        return nullptr;
+    }
+    if (from != SCALAR_F32 && from != SCALAR_F64) return "Only f32/f64 queries can be cast to the index's scalar kind";
+    std::vector<float> row(dims);
+    for (size_t i = 0; i < nq; ++i) {
+        uint8_t const* s = src + i * src_stride;
+        uint8_t* o = dst + i * dst_stride;
+        if (from == SCALAR_F32) std::memcpy(row.data(), s, dims * 4);
+        else
+            for (size_t j = 0; j < dims; ++j) { double v; std::memcpy(&v, s + j * 8, 8); row[j] = (float)v; }
+        switch (to) {
+        case SCALAR_F32: std::memcpy(o, row.data(), dims * 4); break;
+        case SCALAR_F16:
+            for (size_t j = 0; j < dims; ++j) { uint16_t h = f32_to_f16_rn(row[j]); std::memcpy(o + 2 * j, &h, 2); }
+            break;
+        case SCALAR_BF16:
+            for (size_t j = 0; j < dims; ++j) { uint16_t h = f32_to_bf16_rn(row[j]); std::memcpy(o + 2 * j, &h, 2); }
+            break;
+        case SCALAR_I8: { /* cast_to_i8_gt, index_plugins.hpp:1172-1191 */
+            double magnitude = 0;
+            for (size_t j = 0; j < dims; ++j) magnitude += (double)row[j] * (double)row[j];
+            magnitude = std::sqrt(magnitude);
+            for (size_t j = 0; j < dims; ++j) {
+                double v = row[j] * 127.0 / magnitude;
+                v = v > 127.0 ? 127.0 : (v < -127.0 ? -127.0 : v);
+                reinterpret_cast<int8_t*>(o)[j] = (int8_t)v;
+            }
+            break;
+        }
+        case SCALAR_B1: /* cast_to_b1x8_gt, index_plugins.hpp:1139-1158 */
+            std::memset(o, 0, to_bytes);
+            for (size_t j = 0; j < dims; ++j)
+                if (row[j] > 0) o[j / 8] |= (uint8_t)(128 >> (j & 7));
+            break;
+        default: return "Unsupported scalar kind";
+        }
+    }
+    return nullptr;
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/*  batched search on host buffers: H2D + kernel + D2H inside the call                            */
+/* ---------------------------------------------------------------------------------------------- */
+
+char const* frozen_index_t::search_host(void const* q, size_t nq, size_t stride, uint32_t query_scalar, size_t k,
+                                        uint64_t* keys, size_t keys_stride, float* dists, size_t dists_stride,
+                                        size_t* counts, uint64_t* computed_out, uint64_t* cycles_out, size_t* total) {
+    if (total) *total = 0;
+    if (!loaded) return "Index is empty: load a serialized index first";
+    if (nq == 0 || k == 0) return nullptr;
+    if (char const* e = ensure_context()) return e;
+    std::lock_guard<std::mutex> lock(mutex);
+    size_t const vs = d.vec_stride ? d.vec_stride : 16, bpv = d.bytes_per_vector;
+
+    if (char const* e = queries.reserve(nq * vs)) return e;
+    if (char const* e = out_keys.reserve(nq * k)) return e;
+    if (char const* e = out_dists.reserve(nq * k)) return e;
+    if (char const* e = counts_reserve_all(nq)) return e;
+
+    /* queries -> device, rows padded to vec_stride */
+    if (vs != bpv) CU(cudaMemsetAsync(queries.ptr, 0, nq * vs, stream));
+    if (query_scalar == scalar) {
+        CU(cudaMemcpy2DAsync(queries.ptr, vs, q, stride, bpv, nq, cudaMemcpyHostToDevice, stream));
+    } else {
+        if (char const* e = h_queries.reserve(nq * vs)) return e;
+        if (char const* e = cast_queries(query_scalar, scalar, dimensions, static_cast<uint8_t const*>(q), stride, nq,
+                                         h_queries.ptr, vs))
+            return e;
+        CU(cudaMemcpy2DAsync(queries.ptr, vs, h_queries.ptr, vs, bpv, nq, cudaMemcpyHostToDevice, stream));
+    }
+
+    bool const want_stats = computed_out || cycles_out;
+    if (char const* e = search_device(queries.ptr, nq, vs, k, out_keys.ptr, out_dists.ptr, this->counts.ptr,
+                                      want_stats ? computed.ptr : nullptr, want_stats ? cycles.ptr : nullptr, stream))
+        return e;
+
+    /* results -> host */
+    bool const dense = keys_stride == k * 8 && dists_stride == k * 4;
+    if (dense) {
+        CU(cudaMemcpyAsync(keys, out_keys.ptr, nq * k * 8, cudaMemcpyDeviceToHost, stream));
+        CU(cudaMemcpyAsync(dists, out_dists.ptr, nq * k * 4, cudaMemcpyDeviceToHost, stream));
+    } else {
+        CU(cudaMemcpy2DAsync(keys, keys_stride, out_keys.ptr, k * 8, k * 8, nq, cudaMemcpyDeviceToHost, stream));
+        CU(cudaMemcpy2DAsync(dists, dists_stride, out_dists.ptr, k * 4, k * 4, nq, cudaMemcpyDeviceToHost, stream));
+    }
+    CU(cudaMemcpyAsync(h_counts.ptr, this->counts.ptr, nq * 4, cudaMemcpyDeviceToHost, stream));
+    if (want_stats) {
+        CU(cudaMemcpyAsync(h_computed.ptr, computed.ptr, nq * 4, cudaMemcpyDeviceToHost, stream));
+        CU(cudaMemcpyAsync(h_cycles.ptr, cycles.ptr, nq * 4, cudaMemcpyDeviceToHost, stream));
+    }
+    CU(cudaStreamSynchronize(stream));
+    size_t sum = 0;
+    for (size_t i = 0; i < nq; ++i) {
+        sum += h_counts.ptr[i];
+        if (counts) counts[i] = h_counts.ptr[i];
+        if (computed_out) computed_out[i] = h_computed.ptr[i];
+        if (cycles_out) cycles_out[i] = h_cycles.ptr[i];
+    }
+    if (total) *total = sum;
+    return nullptr;
+}
+
+} // namespace usearch_b200

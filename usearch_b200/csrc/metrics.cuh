@@ -1,0 +1,259 @@
+/*
+ *  metrics.cuh — SimSIMD's distance kernels re-expressed for a sub-warp of LPV lanes walking one
+ *  stored vector with 128-bit loads (metric_punned_t, index_plugins.hpp:1678-2015, resolves the
+ *  builtin metrics to these SimSIMD kernels at index_plugins.hpp:1863-1916).
+ *
+ *  Parity contract: every floating-point kernel reproduces the SUMMATION ORDER of the SimSIMD
+ *  kernel it replaces, using explicit round-to-nearest intrinsics so that nvcc neither contracts
+ *  nor re-associates anything. Integer kernels are exact in any order.
+ *
+ *    f32  : 16 virtual accumulators, element i -> accumulator i mod 16, one fma per element
+ *           (spatial.h:1520-1542 l2sq_f32_skylake, :1587-1615 cos_f32_skylake,
+ *           dot.h:1297-1318 dot_f32_skylake). A 16-byte chunk j holds elements 4j..4j+3, i.e.
+ *           accumulators 4(j mod 4)..+3, so exactly FOUR lanes share a vector: lane `sub` owns
+ *           chunks sub, sub+4, ... and accumulators 4*sub..4*sub+3. The horizontal reduce
+ *           (dot.h:1279-1284) r_i = (v[i]+v[i+8]) + (v[i+4]+v[i+12]); (r0+r1)+(r2+r3) becomes two
+ *           xor-shuffles (2 then 1) and three adds.
+ *    cos  : normalisation is the IEEE restatement 1 - ab*(1/sqrt(a2))*(1/sqrt(b2)) in f64 with
+ *           SimSIMD's zero rules and clamp (spatial.h:1544-1585 uses rsqrt14+Newton, which differs
+ *           by <= 1 ULP(f32) and cannot be reproduced off-x86; see oracle/metrics_pinned.h).
+ *    ip   : 1.0f - dot in f32 (index_plugins.hpp:1914-1916: the f64 result is cast to f32 first).
+ *    i8   : exact i32 sums via dp4a (dot.h:1749-1775, spatial.h:1880-1972).
+ *    b1   : exact popcounts (binary.h:92-105, :271-347).
+ */
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include "device_index.h"
+
+namespace usearch_b200 {
+
+__device__ __forceinline__ uint4 ldg_stream(uint4 const* p) {
+    /* vectors are touched once per query: keep them out of L1 */
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+template <int LPV> __device__ __forceinline__ int reduce_add_i32(int v) {
+#pragma unroll
+    for (int o = LPV / 2; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+/* ---- f32 -------------------------------------------------------------------------------- */
+
+__device__ __forceinline__ float reduce16_f32(float const v[4]) {
+    /* lanes sub=0..3 of a 4-lane group hold accumulators 4*sub..4*sub+3 */
+    float u[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        float t = __fadd_rn(v[c], __shfl_xor_sync(0xffffffffu, v[c], 2)); /* v[i]+v[i+8] | v[i+4]+v[i+12] */
+        u[c] = __fadd_rn(t, __shfl_xor_sync(0xffffffffu, t, 1));
+    }
+    return __fadd_rn(__fadd_rn(u[0], u[1]), __fadd_rn(u[2], u[3]));
+}
+
+__device__ __forceinline__ float cos_normalize_f64(float ab_f, float a2_f, float b2_f) {
+    double ab = (double)ab_f, a2 = (double)a2_f, b2 = (double)b2_f;
+    if (a2 == 0 && b2 == 0) return 0.f;
+    if (ab == 0) return 1.f;
+    double ra = __drcp_rn(__dsqrt_rn(a2));
+    double rb = __drcp_rn(__dsqrt_rn(b2));
+    double r = __dsub_rn(1.0, __dmul_rn(__dmul_rn(ab, ra), rb));
+    return r > 0 ? __double2float_rn(r) : 0.f;
+}
+
+__device__ __forceinline__ float cos_normalize_f32(float ab, float a2, float b2) {
+    if (a2 == 0.0f && b2 == 0.0f) return 0.0f;
+    if (ab == 0.0f) return 1.0f;
+    float ra = __frcp_rn(__fsqrt_rn(a2));
+    float rb = __frcp_rn(__fsqrt_rn(b2));
+    float r = __fsub_rn(1.0f, __fmul_rn(__fmul_rn(ab, ra), rb));
+    return r > 0 ? r : 0.f;
+}
+
+struct l2sq_f32_t {
+    static constexpr int LPV = 4;
+    struct acc_t { float v[4]; };
+    struct qconst_t {};
+    static __device__ __forceinline__ void init(acc_t& a) { a.v[0] = a.v[1] = a.v[2] = a.v[3] = 0.f; }
+    static __device__ __forceinline__ void step(acc_t& a, uint4 b, uint4 q) {
+        float x;
+        x = __fsub_rn(__uint_as_float(q.x), __uint_as_float(b.x)); a.v[0] = __fmaf_rn(x, x, a.v[0]);
+        x = __fsub_rn(__uint_as_float(q.y), __uint_as_float(b.y)); a.v[1] = __fmaf_rn(x, x, a.v[1]);
+        x = __fsub_rn(__uint_as_float(q.z), __uint_as_float(b.z)); a.v[2] = __fmaf_rn(x, x, a.v[2]);
+        x = __fsub_rn(__uint_as_float(q.w), __uint_as_float(b.w)); a.v[3] = __fmaf_rn(x, x, a.v[3]);
+    }
+    static __device__ __forceinline__ float finish(acc_t const& a, qconst_t) { return reduce16_f32(a.v); }
+    static __device__ __forceinline__ qconst_t prepare(uint4 const*, uint32_t, int) { return {}; }
+};
+
+struct ip_f32_t {
+    static constexpr int LPV = 4;
+    struct acc_t { float v[4]; };
+    struct qconst_t {};
+    static __device__ __forceinline__ void init(acc_t& a) { a.v[0] = a.v[1] = a.v[2] = a.v[3] = 0.f; }
+    static __device__ __forceinline__ void step(acc_t& a, uint4 b, uint4 q) {
+        a.v[0] = __fmaf_rn(__uint_as_float(q.x), __uint_as_float(b.x), a.v[0]);
+        a.v[1] = __fmaf_rn(__uint_as_float(q.y), __uint_as_float(b.y), a.v[1]);
+        a.v[2] = __fmaf_rn(__uint_as_float(q.z), __uint_as_float(b.z), a.v[2]);
+        a.v[3] = __fmaf_rn(__uint_as_float(q.w), __uint_as_float(b.w), a.v[3]);
+    }
+    static __device__ __forceinline__ float finish(acc_t const& a, qconst_t) {
+        return __fsub_rn(1.0f, reduce16_f32(a.v));
+    }
+    static __device__ __forceinline__ qconst_t prepare(uint4 const*, uint32_t, int) { return {}; }
+};
+
+struct cos_f32_t {
+    static constexpr int LPV = 4;
+    struct acc_t { float ab[4], b2[4]; };
+    struct qconst_t { float a2; };
+    static __device__ __forceinline__ void init(acc_t& a) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) a.ab[c] = a.b2[c] = 0.f;
+    }
+    static __device__ __forceinline__ void step(acc_t& a, uint4 b, uint4 q) {
+        float bx = __uint_as_float(b.x), by = __uint_as_float(b.y), bz = __uint_as_float(b.z), bw = __uint_as_float(b.w);
+        a.ab[0] = __fmaf_rn(__uint_as_float(q.x), bx, a.ab[0]); a.b2[0] = __fmaf_rn(bx, bx, a.b2[0]);
+        a.ab[1] = __fmaf_rn(__uint_as_float(q.y), by, a.ab[1]); a.b2[1] = __fmaf_rn(by, by, a.b2[1]);
+        a.ab[2] = __fmaf_rn(__uint_as_float(q.z), bz, a.ab[2]); a.b2[2] = __fmaf_rn(bz, bz, a.b2[2]);
+        a.ab[3] = __fmaf_rn(__uint_as_float(q.w), bw, a.ab[3]); a.b2[3] = __fmaf_rn(bw, bw, a.b2[3]);
+    }
+    static __device__ __forceinline__ float finish(acc_t const& a, qconst_t qc) {
+        float ab = reduce16_f32(a.ab);
+        float b2 = reduce16_f32(a.b2);
+        return cos_normalize_f64(ab, qc.a2, b2);
+    }
+    /* a2 = dot(q, q) in the same 16-accumulator order; every 4-lane group computes the same value */
+    static __device__ __forceinline__ qconst_t prepare(uint4 const* q4, uint32_t chunks16, int lane) {
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        for (uint32_t j = lane & 3; j < chunks16; j += 4) {
+            uint4 q = q4[j];
+            v[0] = __fmaf_rn(__uint_as_float(q.x), __uint_as_float(q.x), v[0]);
+            v[1] = __fmaf_rn(__uint_as_float(q.y), __uint_as_float(q.y), v[1]);
+            v[2] = __fmaf_rn(__uint_as_float(q.z), __uint_as_float(q.z), v[2]);
+            v[3] = __fmaf_rn(__uint_as_float(q.w), __uint_as_float(q.w), v[3]);
+        }
+        return {reduce16_f32(v)};
+    }
+};
+
+/* ---- i8 --------------------------------------------------------------------------------- */
+
+template <int LPV_> struct ip_i8_t {
+    static constexpr int LPV = LPV_;
+    struct acc_t { int ab; };
+    struct qconst_t {};
+    static __device__ __forceinline__ void init(acc_t& a) { a.ab = 0; }
+    static __device__ __forceinline__ void step(acc_t& a, uint4 b, uint4 q) {
+        a.ab = __dp4a((int)q.x, (int)b.x, a.ab);
+        a.ab = __dp4a((int)q.y, (int)b.y, a.ab);
+        a.ab = __dp4a((int)q.z, (int)b.z, a.ab);
+        a.ab = __dp4a((int)q.w, (int)b.w, a.ab);
+    }
+    static __device__ __forceinline__ float finish(acc_t const& a, qconst_t) {
+        int ab = reduce_add_i32<LPV>(a.ab);
+        return __fsub_rn(1.0f, __int2float_rn(ab));
+    }
+    static __device__ __forceinline__ qconst_t prepare(uint4 const*, uint32_t, int) { return {}; }
+};
+
+template <int LPV_> struct l2sq_i8_t {
+    static constexpr int LPV = LPV_;
+    struct acc_t { int d2; };
+    struct qconst_t {};
+    static __device__ __forceinline__ void init(acc_t& a) { a.d2 = 0; }
+    static __device__ __forceinline__ void word(acc_t& a, uint32_t b, uint32_t q) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int x = (int)(int8_t)(q >> (8 * i)) - (int)(int8_t)(b >> (8 * i));
+            a.d2 += x * x;
+        }
+    }
+    static __device__ __forceinline__ void step(acc_t& a, uint4 b, uint4 q) {
+        word(a, b.x, q.x); word(a, b.y, q.y); word(a, b.z, q.z); word(a, b.w, q.w);
+    }
+    static __device__ __forceinline__ float finish(acc_t const& a, qconst_t) {
+        return (float)reduce_add_i32<LPV>(a.d2);
+    }
+    static __device__ __forceinline__ qconst_t prepare(uint4 const*, uint32_t, int) { return {}; }
+};
+
+template <int LPV_> struct cos_i8_t {
+    static constexpr int LPV = LPV_;
+    struct acc_t { int ab, b2; };
+    struct qconst_t { int a2; };
+    static __device__ __forceinline__ void init(acc_t& a) { a.ab = a.b2 = 0; }
+    static __device__ __forceinline__ void step(acc_t& a, uint4 b, uint4 q) {
+        a.ab = __dp4a((int)q.x, (int)b.x, a.ab); a.b2 = __dp4a((int)b.x, (int)b.x, a.b2);
+        a.ab = __dp4a((int)q.y, (int)b.y, a.ab); a.b2 = __dp4a((int)b.y, (int)b.y, a.b2);
+        a.ab = __dp4a((int)q.z, (int)b.z, a.ab); a.b2 = __dp4a((int)b.z, (int)b.z, a.b2);
+        a.ab = __dp4a((int)q.w, (int)b.w, a.ab); a.b2 = __dp4a((int)b.w, (int)b.w, a.b2);
+    }
+    static __device__ __forceinline__ float finish(acc_t const& a, qconst_t qc) {
+        int ab = reduce_add_i32<LPV>(a.ab), b2 = reduce_add_i32<LPV>(a.b2);
+        return cos_normalize_f32((float)ab, (float)qc.a2, (float)b2);
+    }
+    static __device__ __forceinline__ qconst_t prepare(uint4 const* q4, uint32_t chunks16, int lane) {
+        int a2 = 0;
+        for (uint32_t j = lane; j < chunks16; j += 32) {
+            uint4 q = q4[j];
+            a2 = __dp4a((int)q.x, (int)q.x, a2); a2 = __dp4a((int)q.y, (int)q.y, a2);
+            a2 = __dp4a((int)q.z, (int)q.z, a2); a2 = __dp4a((int)q.w, (int)q.w, a2);
+        }
+        return {reduce_add_i32<32>(a2)};
+    }
+};
+
+/* ---- b1x8 ------------------------------------------------------------------------------- */
+
+template <int LPV_> struct hamming_b1_t {
+    static constexpr int LPV = LPV_;
+    struct acc_t { int d; };
+    struct qconst_t {};
+    static __device__ __forceinline__ void init(acc_t& a) { a.d = 0; }
+    static __device__ __forceinline__ void step(acc_t& a, uint4 b, uint4 q) {
+        a.d += __popc(b.x ^ q.x) + __popc(b.y ^ q.y) + __popc(b.z ^ q.z) + __popc(b.w ^ q.w);
+    }
+    static __device__ __forceinline__ float finish(acc_t const& a, qconst_t) { return (float)reduce_add_i32<LPV>(a.d); }
+    static __device__ __forceinline__ qconst_t prepare(uint4 const*, uint32_t, int) { return {}; }
+};
+
+template <int LPV_> struct tanimoto_b1_t {
+    static constexpr int LPV = LPV_;
+    struct acc_t { int and_, or_; };
+    struct qconst_t {};
+    static __device__ __forceinline__ void init(acc_t& a) { a.and_ = a.or_ = 0; }
+    static __device__ __forceinline__ void step(acc_t& a, uint4 b, uint4 q) {
+        a.and_ += __popc(b.x & q.x) + __popc(b.y & q.y) + __popc(b.z & q.z) + __popc(b.w & q.w);
+        a.or_ += __popc(b.x | q.x) + __popc(b.y | q.y) + __popc(b.z | q.z) + __popc(b.w | q.w);
+    }
+    static __device__ __forceinline__ float finish(acc_t const& a, qconst_t) {
+        int and_ = reduce_add_i32<LPV>(a.and_), or_ = reduce_add_i32<LPV>(a.or_);
+        return or_ ? __double2float_rn(__dsub_rn(1.0, __ddiv_rn((double)and_, (double)or_))) : 1.f;
+    }
+    static __device__ __forceinline__ qconst_t prepare(uint4 const*, uint32_t, int) { return {}; }
+};
+
+template <int LPV_> struct sorensen_b1_t {
+    static constexpr int LPV = LPV_;
+    struct acc_t { int and_, any_; };
+    struct qconst_t {};
+    static __device__ __forceinline__ void init(acc_t& a) { a.and_ = a.any_ = 0; }
+    static __device__ __forceinline__ void step(acc_t& a, uint4 b, uint4 q) {
+        a.and_ += __popc(b.x & q.x) + __popc(b.y & q.y) + __popc(b.z & q.z) + __popc(b.w & q.w);
+        a.any_ += __popc(b.x) + __popc(b.y) + __popc(b.z) + __popc(b.w) + __popc(q.x) + __popc(q.y) + __popc(q.z) + __popc(q.w);
+    }
+    static __device__ __forceinline__ float finish(acc_t const& a, qconst_t) {
+        int and_ = reduce_add_i32<LPV>(a.and_), any_ = reduce_add_i32<LPV>(a.any_);
+        return __fsub_rn(1.f, __fdiv_rn(__fmul_rn(2.f, (float)and_), (float)any_));
+    }
+    static __device__ __forceinline__ qconst_t prepare(uint4 const*, uint32_t, int) { return {}; }
+};
+
+} // namespace usearch_b200

@@ -1,0 +1,335 @@
+"""Host-side mirror of the reference's Python search API over the C ABI.
+
+Mirrors, for the search path only, ``usearch.index.Index`` (/root/reference/python/usearch/index.py):
+``Index.search`` (index.py:700-748) → ``_search_in_compiled`` (:191-231) → ``search_many``
+(python/lib.cpp:415-461), and the result containers ``Matches`` / ``BatchMatches`` (:300-396).
+Same argument names and meaning, same shapes and dtypes of the results, same padding of short
+rows. Everything below goes through ``libusearch_b200.so`` with plain pointers (ctypes); there is
+no CPU fallback: without the CUDA library or without a GPU the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import Optional, Union
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libusearch_b200.so")
+
+# usearch.h:40-62 ordinals
+METRIC_KIND = {"cos": 1, "ip": 2, "l2sq": 3, "haversine": 4, "divergence": 5, "pearson": 6, "jaccard": 7,
+               "hamming": 8, "tanimoto": 9, "sorensen": 10}
+SCALAR_KIND = {"f32": 1, "f64": 2, "f16": 3, "i8": 4, "b1": 5, "bf16": 6}
+_NP_TO_SCALAR = {np.dtype(np.float32): "f32", np.dtype(np.float64): "f64", np.dtype(np.float16): "f16",
+                 np.dtype(np.int8): "i8", np.dtype(np.uint8): "b1"}
+_BITS = {"f32": 32, "f64": 64, "f16": 16, "bf16": 16, "i8": 8, "b1": 1}
+
+
+class _InitOptions(C.Structure):  # usearch.h:64-110
+    _fields_ = [("metric_kind", C.c_int), ("metric", C.c_void_p), ("quantization", C.c_int),
+                ("dimensions", C.c_size_t), ("connectivity", C.c_size_t), ("expansion_add", C.c_size_t),
+                ("expansion_search", C.c_size_t), ("multi", C.c_bool)]
+
+
+_lib: Optional[C.CDLL] = None
+
+EXPORTED_SYMBOLS = [
+    "usearch_version", "usearch_init", "usearch_free", "usearch_memory_usage", "usearch_hardware_acceleration",
+    "usearch_serialized_length", "usearch_save", "usearch_load", "usearch_view", "usearch_metadata",
+    "usearch_save_buffer", "usearch_load_buffer", "usearch_view_buffer", "usearch_metadata_buffer", "usearch_size",
+    "usearch_capacity", "usearch_dimensions", "usearch_connectivity", "usearch_reserve", "usearch_expansion_add",
+    "usearch_expansion_search", "usearch_change_expansion_add", "usearch_change_expansion_search",
+    "usearch_change_threads_add", "usearch_change_threads_search", "usearch_change_metric_kind",
+    "usearch_change_metric", "usearch_add", "usearch_contains", "usearch_count", "usearch_search",
+    "usearch_filtered_search", "usearch_get", "usearch_remove", "usearch_rename", "usearch_distance",
+    "usearch_exact_search", "usearch_clear",
+    # additive
+    "usearch_search_many", "usearch_b200_search_many_device", "usearch_b200_search_many_stats",
+    "usearch_b200_device", "usearch_b200_kernel_launches", "usearch_b200_last_kernel_ms",
+    "usearch_b200_bytes_per_vector", "usearch_b200_max_level",
+]
+
+
+def load_library() -> C.CDLL:
+    """Load the CUDA library. Fails loudly: there is no pure-Python or CPU implementation behind it."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(nvcc, sm_100a). The B200 backend has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    err = C.POINTER(C.c_char_p)
+    lib.usearch_version.restype = C.c_char_p
+    lib.usearch_init.restype = C.c_void_p
+    lib.usearch_init.argtypes = [C.POINTER(_InitOptions), err]
+    lib.usearch_free.argtypes = [C.c_void_p, err]
+    lib.usearch_hardware_acceleration.restype = C.c_char_p
+    lib.usearch_hardware_acceleration.argtypes = [C.c_void_p, err]
+    for name in ("usearch_memory_usage", "usearch_serialized_length", "usearch_size", "usearch_capacity",
+                 "usearch_dimensions", "usearch_connectivity", "usearch_expansion_add", "usearch_expansion_search"):
+        getattr(lib, name).restype = C.c_size_t
+        getattr(lib, name).argtypes = [C.c_void_p, err]
+    for name in ("usearch_change_expansion_add", "usearch_change_expansion_search"):
+        getattr(lib, name).argtypes = [C.c_void_p, C.c_size_t, err]
+    for name in ("usearch_save", "usearch_load", "usearch_view"):
+        getattr(lib, name).argtypes = [C.c_void_p, C.c_char_p, err]
+    for name in ("usearch_save_buffer", "usearch_load_buffer", "usearch_view_buffer"):
+        getattr(lib, name).argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, err]
+    lib.usearch_metadata_buffer.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(_InitOptions), err]
+    lib.usearch_metadata.argtypes = [C.c_char_p, C.POINTER(_InitOptions), err]
+    lib.usearch_clear.argtypes = [C.c_void_p, err]
+    lib.usearch_add.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int, err]
+    lib.usearch_search.restype = C.c_size_t
+    lib.usearch_search.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, err]
+    lib.usearch_search_many.restype = C.c_size_t
+    lib.usearch_search_many.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_size_t,
+                                        C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, err]
+    lib.usearch_b200_search_many_stats.restype = C.c_size_t
+    lib.usearch_b200_search_many_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int,
+                                                   C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                   C.c_void_p, err]
+    lib.usearch_b200_search_many_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t,
+                                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                    C.c_void_p, err]
+    lib.usearch_b200_device.argtypes = [C.c_void_p]
+    lib.usearch_b200_kernel_launches.restype = C.c_uint64
+    lib.usearch_b200_kernel_launches.argtypes = [C.c_void_p]
+    lib.usearch_b200_last_kernel_ms.restype = C.c_float
+    lib.usearch_b200_last_kernel_ms.argtypes = [C.c_void_p]
+    lib.usearch_b200_bytes_per_vector.restype = C.c_size_t
+    lib.usearch_b200_bytes_per_vector.argtypes = [C.c_void_p]
+    lib.usearch_b200_max_level.restype = C.c_size_t
+    lib.usearch_b200_max_level.argtypes = [C.c_void_p]
+    _lib = lib
+    return lib
+
+
+def _raise(err: C.c_char_p) -> None:
+    if err.value:
+        raise RuntimeError(err.value.decode())
+
+
+@dataclass
+class Matches:
+    """Single-query result (index.py:300-330): ``keys`` and ``distances`` trimmed to the found count."""
+    keys: np.ndarray
+    distances: np.ndarray
+    visited_members: int = 0
+    computed_distances: int = 0
+
+    def __len__(self) -> int:
+        return len(self.keys)
+
+    def to_list(self):
+        return [(int(k), float(d)) for k, d in zip(self.keys, self.distances)]
+
+
+@dataclass
+class BatchMatches:
+    """Batch result (index.py:333-396): dense ``[nq, count]`` matrices + per-row ``counts``."""
+    keys: np.ndarray
+    distances: np.ndarray
+    counts: np.ndarray
+    visited_members: int = 0
+    computed_distances: int = 0
+
+    def __len__(self) -> int:
+        return len(self.counts)
+
+    def __getitem__(self, i: int) -> Matches:
+        n = int(self.counts[i])
+        return Matches(self.keys[i, :n], self.distances[i, :n])
+
+    def to_list(self):
+        return [self[i].to_list() for i in range(len(self))]
+
+    def mean_recall(self, expected: np.ndarray, count: Optional[int] = None) -> float:
+        return float(self.count_matches(expected, count)) / len(expected)
+
+    def count_matches(self, expected: np.ndarray, count: Optional[int] = None) -> int:
+        """index.py:379-393: is ``expected[i]`` anywhere among the first ``count`` results of row i."""
+        hits = 0
+        for i in range(len(expected)):
+            n = int(self.counts[i]) if count is None else min(count, int(self.counts[i]))
+            hits += int(expected[i] in self.keys[i, :n])
+        return hits
+
+
+class Index:
+    """Search-side drop-in for ``usearch.index.Index`` whose graph lives frozen in B200 HBM.
+
+    Build the graph with the reference (or load a ``.usearch`` file), then ``load``/``view``/``restore``
+    it here; ``search`` runs the whole batch as one persistent-kernel launch.
+    """
+
+    def __init__(self, *, ndim: int = 0, metric: str = "cos", dtype: str = "f32", connectivity: int = 16,
+                 expansion_add: int = 128, expansion_search: int = 64, multi: bool = False,
+                 path: Optional[str] = None, view: bool = False):
+        self._lib = load_library()
+        err = C.c_char_p()
+        if ndim:
+            opts = _InitOptions(METRIC_KIND[metric], None, SCALAR_KIND[dtype], ndim, connectivity, expansion_add,
+                                expansion_search, multi)
+            self._h = C.c_void_p(self._lib.usearch_init(C.byref(opts), C.byref(err)))
+        else:
+            self._h = C.c_void_p(self._lib.usearch_init(None, C.byref(err)))
+        _raise(err)
+        self._dtype = dtype
+        self._expansion_search = expansion_search
+        self._keepalive = None
+        if path is not None:
+            (self.view if view else self.load)(path)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._lib.usearch_free(self._h, None)
+            self._h = None
+
+    # ---- loading (index.py:1100-1200 `load`/`view`/`restore`) ------------------------------------
+    @staticmethod
+    def restore(path_or_buffer, view: bool = False) -> "Index":
+        index = Index()
+        (index.view if view else index.load)(path_or_buffer)
+        return index
+
+    def load(self, path_or_buffer: Union[str, os.PathLike, bytes, bytearray, np.ndarray]) -> "Index":
+        err = C.c_char_p()
+        if isinstance(path_or_buffer, (str, os.PathLike)):
+            self._lib.usearch_load(self._h, os.fspath(path_or_buffer).encode(), C.byref(err))
+            meta = self.metadata(path_or_buffer)
+        else:
+            buf = np.frombuffer(path_or_buffer, dtype=np.uint8) if not isinstance(path_or_buffer, np.ndarray) \
+                else np.ascontiguousarray(path_or_buffer, dtype=np.uint8)
+            self._lib.usearch_load_buffer(self._h, buf.ctypes.data_as(C.c_void_p), buf.size, C.byref(err))
+            meta = self.metadata(buf) if not err.value else None
+        _raise(err)
+        self._dtype = meta["dtype"]
+        self._lib.usearch_change_expansion_search(self._h, self._expansion_search, None)
+        return self
+
+    view = load  # the device copy never aliases the file: `view` == `load`
+
+    @staticmethod
+    def metadata(path_or_buffer) -> dict:
+        lib = load_library()
+        opts = _InitOptions()
+        err = C.c_char_p()
+        if isinstance(path_or_buffer, (str, os.PathLike)):
+            lib.usearch_metadata(os.fspath(path_or_buffer).encode(), C.byref(opts), C.byref(err))
+        else:
+            buf = np.ascontiguousarray(path_or_buffer, dtype=np.uint8)
+            lib.usearch_metadata_buffer(buf.ctypes.data_as(C.c_void_p), buf.size, C.byref(opts), C.byref(err))
+        _raise(err)
+        inv_m = {v: k for k, v in METRIC_KIND.items()}
+        inv_s = {v: k for k, v in SCALAR_KIND.items()}
+        return {"metric": inv_m.get(opts.metric_kind), "dtype": inv_s.get(opts.quantization),
+                "ndim": opts.dimensions, "multi": bool(opts.multi)}
+
+    def save(self, path: Optional[str] = None) -> Optional[np.ndarray]:
+        err = C.c_char_p()
+        if path is not None:
+            self._lib.usearch_save(self._h, os.fspath(path).encode(), C.byref(err))
+            _raise(err)
+            return None
+        n = self._lib.usearch_serialized_length(self._h, None)
+        buf = np.empty(n, dtype=np.uint8)
+        self._lib.usearch_save_buffer(self._h, buf.ctypes.data_as(C.c_void_p), n, C.byref(err))
+        _raise(err)
+        return buf
+
+    # ---- properties (index.py:1377-1470) -----------------------------------------------------------
+    size = property(lambda s: s._lib.usearch_size(s._h, None))
+    ndim = property(lambda s: s._lib.usearch_dimensions(s._h, None))
+    connectivity = property(lambda s: s._lib.usearch_connectivity(s._h, None))
+    capacity = property(lambda s: s._lib.usearch_capacity(s._h, None))
+    memory_usage = property(lambda s: s._lib.usearch_memory_usage(s._h, None))
+    serialized_length = property(lambda s: s._lib.usearch_serialized_length(s._h, None))
+    hardware_acceleration = property(lambda s: s._lib.usearch_hardware_acceleration(s._h, None).decode())
+    dtype = property(lambda s: s._dtype)
+    max_level = property(lambda s: s._lib.usearch_b200_max_level(s._h))
+    kernel_launches = property(lambda s: s._lib.usearch_b200_kernel_launches(s._h))
+    last_kernel_ms = property(lambda s: s._lib.usearch_b200_last_kernel_ms(s._h))
+    bytes_per_vector = property(lambda s: s._lib.usearch_b200_bytes_per_vector(s._h))
+
+    def __len__(self) -> int:
+        return self.size
+
+    @property
+    def expansion_search(self) -> int:
+        return self._lib.usearch_expansion_search(self._h, None)
+
+    @expansion_search.setter
+    def expansion_search(self, v: int) -> None:
+        self._expansion_search = v
+        self._lib.usearch_change_expansion_search(self._h, v, None)
+
+    def add(self, keys, vectors, **_):
+        err = C.c_char_p()
+        self._lib.usearch_add(self._h, 0, None, 0, C.byref(err))
+        _raise(err)
+
+    # ---- search (index.py:700-748) ---------------------------------------------------------------
+    def _kind_of(self, vectors: np.ndarray) -> str:
+        if vectors.dtype == np.uint16:
+            return "bf16"
+        kind = _NP_TO_SCALAR.get(vectors.dtype)
+        if kind is None:
+            raise TypeError(f"Unsupported query dtype {vectors.dtype}")
+        if kind == "b1" and self._dtype == "i8":
+            return "i8"
+        return kind
+
+    def search(self, vectors: np.ndarray, count: int = 10, *, stats: bool = False) -> Union[Matches, BatchMatches]:
+        """1-D input → :class:`Matches`; 2-D input → :class:`BatchMatches` (index.py:191-231)."""
+        vectors = np.asarray(vectors)
+        single = vectors.ndim == 1
+        if single:
+            vectors = vectors[None, :]
+        if vectors.ndim != 2:
+            raise ValueError("Expects a matrix or a vector")
+        if not vectors.flags.c_contiguous and vectors.strides[1] != vectors.itemsize:
+            vectors = np.ascontiguousarray(vectors)  # rows must be contiguous (python/lib.cpp:426-428)
+        kind = self._kind_of(vectors)
+        expect_cols = (self.ndim * _BITS[kind] + 7) // 8 // vectors.itemsize if kind != "b1" else (self.ndim + 7) // 8
+        if vectors.shape[1] != expect_cols:
+            raise ValueError("The number of columns must match the dimensionality of the index")
+        nq = vectors.shape[0]
+        keys = np.zeros((nq, count), dtype=np.uint64)
+        distances = np.zeros((nq, count), dtype=np.float32)
+        counts = np.zeros(nq, dtype=np.uint64)
+        err = C.c_char_p()
+        vm = cd = 0
+        if stats:
+            computed = np.zeros(nq, dtype=np.uint64)
+            visited = np.zeros(nq, dtype=np.uint64)
+            self._lib.usearch_b200_search_many_stats(
+                self._h, vectors.ctypes.data_as(C.c_void_p), nq, vectors.strides[0], SCALAR_KIND[kind], count,
+                keys.ctypes.data_as(C.c_void_p), distances.ctypes.data_as(C.c_void_p),
+                counts.ctypes.data_as(C.c_void_p), computed.ctypes.data_as(C.c_void_p),
+                visited.ctypes.data_as(C.c_void_p), C.byref(err))
+            _raise(err)
+            self.last_computed, self.last_visited = computed, visited
+            vm, cd = int(visited.sum()), int(computed.sum())
+        else:
+            self._lib.usearch_search_many(
+                self._h, vectors.ctypes.data_as(C.c_void_p), nq, vectors.strides[0], SCALAR_KIND[kind], count,
+                keys.ctypes.data_as(C.c_void_p), keys.strides[0], distances.ctypes.data_as(C.c_void_p),
+                distances.strides[0], counts.ctypes.data_as(C.c_void_p), C.byref(err))
+            _raise(err)
+        if single:
+            n = int(counts[0])
+            return Matches(keys[0, :n], distances[0, :n], vm, cd)
+        return BatchMatches(keys, distances, counts, vm, cd)
+
+    def search_device(self, queries_ptr: int, nq: int, stride: int, count: int, keys_ptr: int, distances_ptr: int,
+                      counts_ptr: int, computed_ptr: int = 0, visited_ptr: int = 0, stream: int = 0) -> None:
+        """Device-resident batch: raw device pointers (e.g. ``tensor.data_ptr()``) and a CUDA stream handle."""
+        err = C.c_char_p()
+        self._lib.usearch_b200_search_many_device(self._h, queries_ptr, nq, stride, count, keys_ptr, distances_ptr,
+                                                  counts_ptr, computed_ptr or None, visited_ptr or None,
+                                                  stream or None, C.byref(err))
+        _raise(err)
