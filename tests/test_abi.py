@@ -1,0 +1,71 @@
+"""CPU tests of the boundary: the shared library loads, exports every symbol the header declares,
+and — with no GPU in this container — fails loudly instead of falling back to a CPU path."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import common
+
+HEADER = os.path.join(common.ROOT, "include", "usearch_b200.h")
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = set(re.findall(r"\b(usearch_[a-z0-9_]+)\s*\(", text))
+    return sorted(n for n in names if not n.endswith("_t"))  # drop the function-pointer typedef
+
+
+def test_library_exports_every_declared_symbol():
+    from usearch_b200 import build
+    from usearch_b200.index import EXPORTED_SYMBOLS, load_library
+    build.build()
+    lib = load_library()
+    declared = declared_symbols()
+    assert len(declared) >= 38 + 8
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/usearch_b200.h but not exported"
+    assert sorted(EXPORTED_SYMBOLS) == declared
+    reference_abi = [s for s in declared if not s.startswith("usearch_b200_") and s != "usearch_search_many"]
+    assert len(reference_abi) == 38  # c/usearch.h:116-481
+
+
+def test_no_product_code_touches_the_oracle():
+    """The product package must never import, link or call anything under oracle/."""
+    pkg = os.path.join(common.ROOT, "usearch_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.replace("oracle/metrics_pinned.h", ""), f"{f} mentions the oracle"
+
+
+def test_init_and_metadata_without_gpu():
+    from usearch_b200.index import Index, load_library
+    lib = load_library()
+    assert lib.usearch_version().decode().startswith("2.21.0")
+    g = np.load(os.path.join(common.GOLDEN, "cos_f32_n2000_d64.npz"))
+    meta = Index.metadata(g["blob"])
+    assert meta == {"metric": "cos", "dtype": "f32", "ndim": 64, "multi": False}
+    with pytest.raises(RuntimeError, match="Magic header mismatch"):
+        Index.metadata(np.zeros(200, dtype=np.uint8))
+    index = Index(ndim=64, metric="cos", dtype="f32", connectivity=16, expansion_search=77)
+    assert index.ndim == 64 and index.connectivity == 16 and index.expansion_search == 77 and index.size == 0
+    assert index.hardware_acceleration == "sm_100a"
+    with pytest.raises(RuntimeError, match="frozen"):
+        index.add(1, np.zeros(64, dtype=np.float32))
+    with pytest.raises(RuntimeError):  # unsupported pair must be refused at init (c/lib.cpp:164-167)
+        Index(ndim=64, metric="haversine", dtype="f32")
+
+
+def test_load_fails_loudly_without_cuda_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from usearch_b200.index import Index
+    g = np.load(os.path.join(common.GOLDEN, "cos_f32_n2000_d64.npz"))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Index.restore(g["blob"])

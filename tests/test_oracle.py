@@ -1,0 +1,139 @@
+"""CPU tests that PIN the oracle: the plain-C restatement (oracle/hnsw_oracle.c) against
+  (a) the committed golden fixtures produced by the unmodified reference (tests/golden/make_golden.py),
+  (b) the tiny known-answer vectors the reference's own test-suites hold,
+  (c) the live reference library when oracle/_ref is available."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import common
+from oracle import bindings
+from usearch_b200 import v2format
+
+FIXTURES = sorted(glob.glob(os.path.join(common.GOLDEN, "*.npz")))
+
+
+def ulp_distance(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    ai = a.view(np.int32).astype(np.int64)
+    bi = b.view(np.int32).astype(np.int64)
+    return np.abs(ai - bi)
+
+
+@pytest.mark.parametrize("path", FIXTURES, ids=[os.path.basename(p)[:-4] for p in FIXTURES])
+def test_port_matches_golden(path):
+    g = np.load(path)
+    port = bindings.PortIndex(g["blob"], int(g["ef"]))
+    keys, dist, counts, computed, visited = port.search(g["queries"], int(g["k"]), threads=4)
+    # pinned arithmetic: everything the reference returned, bit for bit
+    assert np.array_equal(counts, g["counts_pinned"])
+    assert np.array_equal(keys, g["keys_pinned"])
+    assert np.array_equal(dist.view(np.uint32), g["distances_pinned"].view(np.uint32))
+    assert np.array_equal(computed, g["computed_pinned"])
+    assert np.array_equal(visited, g["visited_pinned"])
+    # the reference's NATIVE SimSIMD dispatch on the generating host: same labels, distances <= 1 ULP,
+    # except i8/f16-style cosine whose native kernel uses the 12-bit rsqrt_ps (not among the fixtures)
+    assert np.array_equal(keys, g["keys_native"])
+    found = np.arange(keys.shape[1])[None, :] < counts[:, None]
+    assert ulp_distance(dist, g["distances_native"])[found].max() <= 1
+
+
+def test_golden_has_padding_and_removed_entries():
+    g = np.load(os.path.join(common.GOLDEN, "ip_f32_n1500_d48_removed.npz"))
+    graph = v2format.loads(g["blob"])
+    assert (graph.keys == v2format.FREE_KEY).sum() == 150
+    assert not np.isin(g["keys_pinned"], [v2format.FREE_KEY]).any()
+
+
+def _tiny(metric, scalar, vectors, keys, dims):
+    """Fully connected single-level graph over a handful of vectors."""
+    n = len(keys)
+    nb = [[[j for j in range(n) if j != i]] for i in range(n)]
+    graph = v2format.Graph(metric, scalar, dims, 2 if n <= 3 else n, max(4, 2 * n), np.asarray(vectors), np.asarray(keys, dtype=np.uint64),
+                           np.zeros(n, dtype=np.int16), nb, 0, 0)
+    return v2format.dumps(graph)
+
+
+def test_known_answers_from_reference_tests():
+    # javascript/usearch.test.js:60-84 — l2sq is NOT square-rooted
+    blob = _tiny("l2sq", "f32", np.array([[10, 20], [10, 25]], dtype=np.float32), [15, 16], 2)
+    keys, dist, counts, *_ = bindings.PortIndex(blob).search(np.array([[13, 14]], dtype=np.float32), 2)
+    assert keys.tolist() == [[15, 16]] and dist.tolist() == [[45.0, 130.0]] and counts.tolist() == [2]
+    # golang/lib_test.go:835-877 — cos of orthogonal unit vectors is 1, l2sq is 2, i8 l2sq {10,0,0}/{0,10,0} = 200
+    blob = _tiny("cos", "f32", np.array([[1, 0, 0], [0, 1, 0]], dtype=np.float32), [1, 2], 3)
+    _, dist, *_ = bindings.PortIndex(blob).search(np.array([[1, 0, 0]], dtype=np.float32), 2)
+    assert dist.tolist() == [[0.0, 1.0]]
+    blob = _tiny("l2sq", "i8", np.array([[10, 0, 0], [0, 10, 0]], dtype=np.int8), [1, 2], 3)
+    _, dist, *_ = bindings.PortIndex(blob).search(np.array([[10, 0, 0]], dtype=np.int8), 2)
+    assert dist.tolist() == [[0.0, 200.0]]
+    # cpp/test.cpp:1071-1099 — 1-D l2sq keeps exact key order 42, 43, 44
+    blob = _tiny("l2sq", "f32", np.array([[10.1], [10.2], [10.3]], dtype=np.float32), [42, 43, 44], 1)
+    keys, *_ = bindings.PortIndex(blob).search(np.array([[10.0]], dtype=np.float32), 3)
+    assert keys.tolist() == [[42, 43, 44]]
+
+
+def test_edge_cases_port():
+    # empty index: count 0, padding with key 0 and a signalling NaN (index.hpp:2715-2720)
+    empty = v2format.dumps(v2format.Graph("cos", "f32", 8, 16, 32, np.zeros((0, 32), np.uint8), np.zeros(0, np.uint64),
+                                          np.zeros(0, np.int16), [], 0, 0))
+    keys, dist, counts, *_ = bindings.PortIndex(empty).search(np.ones((2, 8), dtype=np.float32), 3)
+    assert counts.tolist() == [0, 0] and (keys == 0).all() and (dist.view(np.uint32) == 0x7FA00000).all()
+    # fewer members than k: short rows are padded
+    blob = _tiny("l2sq", "f32", np.array([[0.0], [1.0]], dtype=np.float32), [7, 8], 1)
+    keys, dist, counts, *_ = bindings.PortIndex(blob).search(np.array([[0.25]], dtype=np.float32), 5)
+    assert counts.tolist() == [2] and keys[0, :2].tolist() == [7, 8] and (keys[0, 2:] == 0).all()
+    assert np.isnan(dist[0, 2:]).all()
+
+
+@pytest.mark.skipif(not common.have_reference(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("metric,scalar,n,d,m,ef,k", [
+    ("l2sq", "f32", 3000, 24, 16, 64, 10),
+    ("cos", "f32", 2000, 100, 8, 16, 10),      # ef barely above k
+    ("ip", "f32", 1000, 17, 3, 5, 10),        # "absurd" config: M=3, ef < k (cpp/test.cpp:820-865)
+    ("cos", "f16", 1500, 64, 16, 64, 10),
+    ("l2sq", "bf16", 1500, 40, 16, 64, 10),
+    ("ip", "i8", 2000, 128, 16, 64, 10),
+    ("hamming", "b1", 5000, 64, 16, 64, 10),   # 64-bit codes: ties everywhere
+    ("hamming", "b1", 3000, 256, 64, 64, 20),
+    ("sorensen", "b1", 1500, 128, 8, 32, 5),
+])
+def test_port_matches_live_reference(metric, scalar, n, d, m, ef, k):
+    base, q = common.make_collection(n, d, scalar, 200, iid=(d < 32))
+    ref, blob = common.build_reference_blob(base, metric, scalar, d, m, threads=4)
+    ref.pin_metric(True)
+    ref.change_expansion_search(ef)
+    want = ref.search(q, k, threads=4)
+    got = bindings.PortIndex(blob, ef).search(q, k, threads=4)
+    common.assert_same_results(want, got, f"{metric}/{scalar}")
+    # exact (brute-force) path: index.hpp:4251-4268
+    want = ref.search(q[:20], k, threads=2, exact=True)
+    got = bindings.PortIndex(blob, ef).search(q[:20], k, threads=2, exact=True)
+    common.assert_same_results(want[:3], got[:3], f"exact {metric}/{scalar}")
+
+
+@pytest.mark.skipif(not common.have_reference(), reason="oracle/_ref not built")
+def test_pinned_metrics_equal_native_where_exact():
+    """On an AVX-512 host the pinned restatement IS the native kernel for every exactly
+    reproducible metric; cosine differs by the rsqrt approximation only."""
+    rng = np.random.default_rng(7)
+    for metric, scalar, d, exact in [("l2sq", "f32", 768, True), ("ip", "f32", 100, True), ("cos", "f32", 768, False),
+                                     ("ip", "i8", 1024, True), ("l2sq", "i8", 100, True), ("hamming", "b1", 256, True),
+                                     ("tanimoto", "b1", 200, True)]:
+        ref = bindings.RefIndex("parity", metric=metric, scalar=scalar, dims=d, connectivity=4)
+        if ref.isa_name not in ("skylake", "ice", "sapphire", "genoa"):
+            pytest.skip(f"host selects {ref.isa_name} kernels")
+        x = common.datagen.to_scalar(rng.standard_normal((64, d), dtype=np.float32), scalar)
+        native = np.array([ref.distance(x[i], x[i + 1]) for i in range(63)], dtype=np.float32)
+        ref.pin_metric(True)
+        pinned = np.array([ref.distance(x[i], x[i + 1]) for i in range(63)], dtype=np.float32)
+        if exact:
+            assert np.array_equal(native.view(np.uint32), pinned.view(np.uint32)), (metric, scalar)
+        else:
+            assert ulp_distance(native, pinned).max() <= 1, (metric, scalar)
+
+
+def test_v2format_roundtrip():
+    g = np.load(FIXTURES[0])
+    graph = v2format.loads(g["blob"])
+    assert np.array_equal(v2format.dumps(graph), g["blob"])
