@@ -173,6 +173,11 @@ size_t usearch_b200_search_many_stats(usearch_index_t index, void const* queries
 
 /* Introspection for tests / bench: CUDA device ordinal, kernel launches issued so far by this
  * handle, duration in milliseconds of the most recent search kernel (CUDA events on its stream). */
+/* Phase introspection of the search kernel: enable != 0 turns on (and zeroes) sixteen device-side
+ * counters summed over all queries since; `counters16` (may be NULL) first receives the current values:
+ * cycles of setup+descent | heap pop | row + visited test | vector wait | distance math | accept replay |
+ * output, then queries | heap pushes | sum of per-query max heap size | max heap size | 5 reserved. */
+void usearch_b200_profile_phases(usearch_index_t index, int enable, uint64_t* counters16);
 int usearch_b200_device(usearch_index_t index);
 uint64_t usearch_b200_kernel_launches(usearch_index_t index);
 float usearch_b200_last_kernel_ms(usearch_index_t index);

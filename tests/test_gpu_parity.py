@@ -20,6 +20,9 @@ CASES = [
     ("hamming", "b1", 20000, 256, 64, 64, 10, 256),
     ("tanimoto", "b1", 6000, 200, 16, 64, 10, 128),
     ("sorensen", "b1", 6000, 256, 16, 64, 10, 128),
+    ("l2sq", "f32", 5000, 32, 16, 300, 40, 64),     # ef > 256: shared-memory `top`, k > 32, DIRECT kernel
+    ("ip", "f32", 6000, 128, 16, 300, 50, 64),      # ef > 256 on the STAGED (TMA) kernel
+    ("cos", "f32", 4000, 64, 40, 256, 100, 64),     # M0 = 80 > 64 neighbours per row, ef == 256
 ]
 
 
@@ -47,3 +50,31 @@ def test_search_matches_reference(metric, scalar, n, d, m, ef, k, nq):
     common.assert_same_results(want, (got.keys, got.distances, got.counts, index.last_computed, index.last_visited),
                                f"gpu vs reference [{metric}/{scalar}]")
     assert index.kernel_launches >= 1
+
+
+@pytest.mark.parametrize("mode", ["hash", "bitmap"])
+def test_visited_modes_and_scratch_retry(mode):
+    """Both `visits` implementations are exact; in hash mode i.i.d. data overflows the default table for
+    some queries, which exercises the flag-and-retry path (frozen_index_t::search_device)."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import numpy as np, common\n"
+        "from oracle import bindings\n"
+        "from usearch_b200.index import Index\n"
+        "base, q = common.make_collection(30000, 64, 'f32', 512, iid=True)\n"
+        "ref, blob = common.build_reference_blob(base, 'l2sq', 'f32', 64, 16, threads=16)\n"
+        "want = bindings.PortIndex(blob, 64).search(q, 10, threads=16)\n"
+        "index = Index.restore(blob); index.expansion_search = 64\n"
+        "got = index.search(q, 10, stats=True)\n"
+        "common.assert_same_results(want, (got.keys, got.distances, got.counts, index.last_computed, index.last_visited), 'mode')\n"
+        "print('launches', index.kernel_launches, 'maxD', int(want[3].max()))\n"
+    ) % (common.ROOT, os.path.join(common.ROOT, "tests"))
+    env = dict(os.environ, USEARCH_B200_VISITED=mode, USEARCH_B200_SCRATCH_SHRINK="64")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    launches = int(out.stdout.split("launches")[1].split()[0])
+    if mode == "hash":  # bitmap `visits` cannot overflow; its heap head alone (shared memory) holds these searches
+        assert launches >= 2, "expected at least one retry launch with 64x undersized scratch: " + out.stdout

@@ -232,6 +232,8 @@ void usearch_change_metric_kind(usearch_index_t index, usearch_metric_kind_t kin
     uint32_t m = metric_to_char(kind);
     if (!m || !search_supported(m, ix->scalar)) return set_error(error, "Unknown metric kind!");
     std::lock_guard<std::mutex> lock(ix->mutex);
+    if (ix->loaded && search_needs_norms(m, ix->scalar) && !ix->d.norms)
+        return set_error(error, "Changing a frozen index to this metric needs a reload");
     ix->metric = m;
     ix->d.metric = m;
 }
@@ -327,6 +329,17 @@ void usearch_clear(usearch_index_t index, usearch_error_t*) {
     frozen_index_t* ix = as_index(index);
     std::lock_guard<std::mutex> lock(ix->mutex);
     ix->release_device();
+}
+
+void usearch_b200_profile_phases(usearch_index_t index, int enable, uint64_t* counters16) {
+    frozen_index_t* ix = as_index(index);
+    std::lock_guard<std::mutex> lock(ix->mutex);
+    if (counters16) {
+        std::memset(counters16, 0, 128);
+        if (ix->phase_cycles.ptr) cudaMemcpy(counters16, ix->phase_cycles.ptr, 128, cudaMemcpyDeviceToHost);
+    }
+    ix->profile_phases = enable != 0;
+    if (ix->profile_phases && !ix->phase_cycles.reserve(16)) cudaMemset(ix->phase_cycles.ptr, 0, 128);
 }
 
 int usearch_b200_device(usearch_index_t index) { return as_index(index)->device; }

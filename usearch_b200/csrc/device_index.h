@@ -14,6 +14,8 @@
  *                                          one hop reads exactly 4*m0_stride bytes
  *    upper_base   [n] u32                  first row of the node in `upper`, 0xFFFFFFFF if level 0
  *    upper        [rows x m_stride] u32    rows level 1..L of every multi-level node, back to back
+ *    norms        [n] f32                  cos/f32 only: squared norm of every vector, accumulated by
+ *                                          the exact fma chain the metric would use per distance
  *    deleted_bits [ceil(n/32)] u32         bit set when keys[slot] == free_key; NULL when the
  *                                          index holds no removed entries (the common case), which
  *                                          removes the per-candidate key read of
@@ -42,6 +44,7 @@ struct device_index_t {
     uint32_t const* upper_base = nullptr;
     uint32_t const* upper = nullptr;
     uint32_t const* deleted_bits = nullptr;
+    float const* norms = nullptr; /* [n] ||v||^2 in the metric's own summation order (cos f32), else NULL */
     uint64_t vec_stride = 0; /* bytes */
     uint32_t n = 0;
     uint32_t m0 = 0, m0_stride = 0; /* connectivity_base and its row stride (u32 units, multiple of 4) */
@@ -79,12 +82,22 @@ struct search_args_t {
     /* scheduling + scratch */
     uint32_t* work_counter = nullptr;
     uint32_t* visited = nullptr; /* [warps x visited_cap] */
-    uint32_t visited_cap = 0;    /* power of two */
+    uint32_t visited_cap = 0;    /* HASH mode: table entries per warp, power of two */
+    /* BITMAP mode (visited_bitmap_words != 0): `visited` holds one bit per slot, words per warp
+     * (multiple of 4); one atomicOr per neighbour answers "seen before?" in a single round trip */
+    uint32_t visited_bitmap_words = 0;
     cand_t* heap_spill = nullptr; /* [warps x heap_spill_cap] */
     uint32_t heap_spill_cap = 0;
     uint32_t heap_smem_cap = 0;
     /* per-warp shared memory carve-up (bytes) */
     uint32_t smem_per_warp = 0, off_top_d = 0, off_top_s = 0, off_cand_s = 0, off_cand_d = 0, off_heap = 0;
+    /* STAGED kernels: mbarriers and the slots TMA bulk copies land in (stride = 64 mod 128 bytes, so
+     * that the 4-lane groups of a quarter-warp read disjoint banks) */
+    uint32_t off_bars = 0, off_stage = 0, stage_stride = 0;
+    uint32_t stage_sets = 1; /* 2 = double buffered: 2 x (32/LPV) slots, the next pass lands during the math */
+    /* optional introspection: 8 cycle counters summed over all queries (lane 0 clock64 deltas):
+     * setup+descent | heap pop | row + visited test | vector wait | distance math | accept replay | output */
+    unsigned long long* phase_cycles = nullptr;
 };
 
 } // namespace usearch_b200

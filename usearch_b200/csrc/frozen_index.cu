@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace usearch_b200 {
@@ -58,6 +59,7 @@ frozen_index_t::~frozen_index_t() {
     if (stream) cudaStreamDestroy(stream);
     if (ev_begin) cudaEventDestroy(ev_begin);
     if (ev_end) cudaEventDestroy(ev_end);
+    phase_cycles.release();
     visited.release(); work_counter.release(); status.release(); counts.release(); computed.release();
     cycles.release(); retry_list.release(); heap_spill.release(); queries.release(); out_keys.release();
     out_dists.release(); h_queries.release(); h_keys.release(); h_dists.release(); h_counts.release();
@@ -238,10 +240,17 @@ char const* frozen_index_t::load_blob(uint8_t const* blob, size_t length) {
             uint8_t const* list = q + 10;
             uint32_t c0 = std::min<uint32_t>(rd_u32(list), (uint32_t)m0);
             uint32_t* dst0 = h_nbr0.data() + (i - begin) * ix.m0_stride;
+            /* A self-link or a repeated slot in a layer-0 list can never pass `visits.set()` in
+             * search_to_find_in_base_ (index.hpp:4221): the expanded node and the first occurrence are
+             * already marked. Dropping them here changes nothing observable and lets the kernel issue
+             * every visited test of a row at once. */
+            uint32_t kept = 0;
             for (uint32_t j = 0; j < c0; ++j) {
                 uint32_t s = rd_u32(list + 4 + 4 * j);
                 if (s >= n) return "File is corrupted: neighbour slot out of range";
-                dst0[j] = s;
+                bool drop = s == (uint32_t)i;
+                for (uint32_t t = 0; t < kept && !drop; ++t) drop = dst0[t] == s;
+                if (!drop) dst0[kept++] = s;
             }
             list += nb0;
             for (int16_t l = 0; l < levels[i]; ++l, ++row, list += nb) {
@@ -275,6 +284,14 @@ char const* frozen_index_t::load_blob(uint8_t const* blob, size_t length) {
     ix.upper_base = d_upper_base;
     ix.upper = d_upper;
     ix.deleted_bits = d_deleted;
+    if (search_needs_norms(metric, scalar)) {
+        float* d_norms = nullptr;
+        CU(cudaMalloc(&d_norms, (size_t)n * 4)); dev_allocs[6] = d_norms;
+        hbm_bytes += (size_t)n * 4;
+        CU(search_compute_norms(ix, d_norms, stream));
+        CU(cudaStreamSynchronize(stream));
+        ix.norms = d_norms;
+    }
     d = ix;
     loaded = true;
     return nullptr;
@@ -359,37 +376,77 @@ char const* frozen_index_t::plan(uint32_t k, uint32_t visited_cap_override, laun
     ef = std::max(ef, k);                                               /* index.hpp:3052 */
     pl.ef = ef;
     uint32_t const list_cap = round_up(std::max(d.m0, d.m), 32);
+    /* per-warp (= per-CTA) shared memory: query | top | candidates | mbarriers | TMA slots | heap head */
     uint32_t off = 0;
     off += d.chunks16 * 16;          /* query */
-    pl.off_top_d = off; off += round_up(ef * 4, 16);
-    pl.off_top_s = off; off += round_up(ef * 4, 16);
+    uint32_t const top_smem = ef > 256 ? round_up(ef * 4, 16) : 0; /* ef <= 256: `top` lives in registers */
+    pl.off_top_d = off; off += top_smem;
+    pl.off_top_s = off; off += top_smem;
     pl.off_cand_s = off; off += list_cap * 4;
     pl.off_cand_d = off; off += list_cap * 4;
+    pl.off_bars = off; off += 128; /* up to 16 mbarriers */
+    off = round_up(off, 128);
+    pl.off_stage = off;
+    int const slots = search_stage_slots(d); /* slots of one set: 32 / LPV */
+    pl.stage_stride = slots ? round_up((uint32_t)d.vec_stride, 128) + 64 : 0;
+    /* an SM has 228 KB of shared memory and charges 1 KB per resident CTA on top of its request */
+    size_t const smem_sm = 228 * 1024, cta_tax = 1024, smem_cta_max = 227 * 1024;
+    uint32_t const min_heap = 128 * 8;
+    /* double-buffer the TMA slots when at least 4 warps per SM still fit */
+    static int const forced_sets = [] { char const* v = std::getenv("USEARCH_B200_STAGE_SETS"); return v ? std::atoi(v) : 0; }();
+    pl.stage_sets = 1;
+    if (slots) {
+        size_t const two = off + 2 * (size_t)slots * pl.stage_stride + min_heap + cta_tax;
+        pl.stage_sets = (forced_sets == 1 || forced_sets == 2) ? (uint32_t)forced_sets : (smem_sm / two >= 4 ? 2u : 1u);
+    }
+    off += (uint32_t)slots * pl.stage_sets * pl.stage_stride;
     pl.off_heap = off;
     uint32_t const fixed = off;
-    size_t const smem_sm = 227 * 1024;
-    int const wpb = search_warps_per_block();
-    /* aim for 24 resident warps per SM; whatever shared memory is left per warp holds the heap head */
-    uint32_t const target_warps = 24;
-    uint32_t budget = (uint32_t)(smem_sm / target_warps) & ~15u;
-    uint32_t heap_bytes = budget > fixed + 64 * 8 ? budget - fixed : 64 * 8;
-    heap_bytes = std::min<uint32_t>(heap_bytes, 4096 * 8);
-    pl.heap_smem_cap = heap_bytes / 8;
-    pl.smem_per_warp = round_up(fixed + pl.heap_smem_cap * 8, 16);
-    pl.smem_per_block = (size_t)pl.smem_per_warp * wpb;
-    if (pl.smem_per_block > smem_sm) return "Expansion or dimensionality too large for on-chip state";
+    if (fixed + min_heap > smem_cta_max) return "Expansion or dimensionality too large for on-chip state";
+    static int const forced_warps = [] { char const* v = std::getenv("USEARCH_B200_WARPS_PER_SM"); return v ? std::atoi(v) : 0; }();
+    uint32_t warps_sm = (uint32_t)std::min<size_t>(smem_sm / (fixed + min_heap + cta_tax), slots ? 16 : 24);
+    if (forced_warps > 0) warps_sm = std::min<uint32_t>(warps_sm, (uint32_t)forced_warps);
+    warps_sm = std::max(warps_sm, 1u);
+    uint32_t budget = (uint32_t)(smem_sm / warps_sm - cta_tax);
+    budget = std::min<uint32_t>(budget, (uint32_t)smem_cta_max);
+    uint32_t heap_bytes = std::min<uint32_t>((budget - fixed) & ~15u, 4096 * 8);
+    pl.heap_smem_cap = heap_bytes / 8; /* even: heap_bytes is a multiple of 16 */
+    pl.smem_per_warp = fixed + pl.heap_smem_cap * 8;
+    pl.smem_per_block = pl.smem_per_warp;
+    pl.warps_per_sm_target = warps_sm;
 
-    uint64_t want = visited_cap_override ? visited_cap_override : (uint64_t)2 * ef * d.m0;
-    want = std::max<uint64_t>(want, 2048);
-    uint64_t const enough = (uint64_t)2 * ((uint64_t)d.n + d.m0 + 1); /* can never overflow beyond this */
-    pl.visited_cap = ceil2(std::min<uint64_t>(want, enough));
-    pl.visited_cap = std::max<uint32_t>(pl.visited_cap, 64);
-    /* pushes <= visited entries <= cap/2, so this spill can not overflow before `visits` does */
-    pl.heap_spill_cap = pl.visited_cap / 2;
+    /* scratch per warp. `scale` (1, 8, 64, ...) grows it for the retry of overflowed queries. */
+    uint64_t const scale = visited_cap_override ? visited_cap_override : 1;
+    uint64_t const enough = (uint64_t)2 * ((uint64_t)d.n + d.m0 + 1); /* a hash table this large can never overflow */
+    static int const forced = [] { /* test hook: USEARCH_B200_VISITED=hash|bitmap */
+        char const* v = std::getenv("USEARCH_B200_VISITED");
+        return !v ? 0 : (std::strcmp(v, "hash") == 0 ? 1 : (std::strcmp(v, "bitmap") == 0 ? 2 : 0));
+    }();
+    static uint64_t const shrink = [] { /* test hook: start with undersized scratch to exercise the retry path */
+        char const* v = std::getenv("USEARCH_B200_SCRATCH_SHRINK");
+        return v && std::atoi(v) > 0 ? (uint64_t)std::atoi(v) : (uint64_t)1;
+    }();
+    if (forced == 2 || (forced == 0 && (uint64_t)d.n <= BITMAP_MAX_SLOTS)) {
+        /* BITMAP visits: one bit per slot, exact, never overflows */
+        pl.visited_bitmap_words = round_up((d.n + 31) / 32, 4);
+        pl.visited_cap = 0;
+        uint64_t spill = std::max<uint64_t>(1024, (uint64_t)8 * ef) * scale / shrink;
+        spill = std::max<uint64_t>(spill, 16);
+        pl.heap_spill_cap = (uint32_t)std::min<uint64_t>(spill, (uint64_t)d.n + 1);
+        pl.maxed = pl.heap_spill_cap >= d.n;
+    } else {
+        pl.visited_bitmap_words = 0;
+        uint64_t want = std::max<uint64_t>((uint64_t)2 * ef * d.m0 * scale, 2048) / shrink;
+        pl.visited_cap = std::max<uint32_t>(ceil2(std::min<uint64_t>(want, enough)), 64);
+        /* pushes <= visited entries <= cap/2, so this spill can not overflow before `visits` does */
+        pl.heap_spill_cap = pl.visited_cap / 2;
+        pl.maxed = pl.visited_cap >= enough;
+    }
 
     int per_sm = 0;
     CU(search_occupancy(d, &per_sm, pl.smem_per_block));
     if (per_sm < 1) return "Kernel does not fit on an SM";
+    per_sm = std::min<int>(per_sm, (int)pl.warps_per_sm_target);
     pl.blocks = per_sm * sm_count;
     return nullptr;
 }
@@ -415,7 +472,7 @@ char const* frozen_index_t::search_device(void const* d_queries, size_t nq, size
     if (char const* e = work_counter.reserve(2)) return e;
     if (char const* e = status.reserve(nq)) return e;
     if (char const* e = h_status.reserve(nq)) return e;
-    if (char const* e = visited.reserve(warps * pl.visited_cap)) return e;
+    if (char const* e = visited.reserve(warps * pl.visited_words_per_warp())) return e;
     if (char const* e = heap_spill.reserve(warps * pl.heap_spill_cap)) return e;
 
     search_args_t a;
@@ -433,13 +490,20 @@ char const* frozen_index_t::search_device(void const* d_queries, size_t nq, size
     a.work_counter = work_counter.ptr;
     a.visited = visited.ptr;
     a.visited_cap = pl.visited_cap;
+    a.visited_bitmap_words = pl.visited_bitmap_words;
     a.heap_spill = heap_spill.ptr;
     a.heap_spill_cap = pl.heap_spill_cap;
     a.heap_smem_cap = pl.heap_smem_cap;
     a.smem_per_warp = pl.smem_per_warp;
     a.off_top_d = pl.off_top_d; a.off_top_s = pl.off_top_s; a.off_cand_s = pl.off_cand_s;
     a.off_cand_d = pl.off_cand_d; a.off_heap = pl.off_heap;
+    a.off_bars = pl.off_bars; a.off_stage = pl.off_stage; a.stage_stride = pl.stage_stride;
+    a.stage_sets = pl.stage_sets;
 
+    if (profile_phases) {
+        if (char const* e = phase_cycles.reserve(16)) return e;
+        a.phase_cycles = phase_cycles.ptr;
+    }
     CU(cudaMemsetAsync(work_counter.ptr, 0, 8, s));
     CU(cudaEventRecord(ev_begin, s));
     CU(search_launch(d, a, blocks, pl.smem_per_block, s));
@@ -453,27 +517,32 @@ char const* frozen_index_t::search_device(void const* d_queries, size_t nq, size
     std::vector<uint32_t> failed;
     for (size_t i = 0; i < nq; ++i)
         if (h_status.ptr[i] != STATUS_OK) failed.push_back((uint32_t)i);
-    uint32_t cap = pl.visited_cap;
-    uint64_t const enough = (uint64_t)2 * ((uint64_t)d.n + d.m0 + 1);
+    uint64_t scale = 1;
+    bool maxed = pl.maxed;
     while (!failed.empty()) {
-        if (cap >= enough) return "Search scratch overflow that a full-size table could not fix";
+        if (maxed) return "Search scratch overflow that full-size scratch could not fix";
+        scale *= 8;
         launch_plan_t rp;
-        if (char const* e = plan((uint32_t)k, (uint32_t)std::min<uint64_t>((uint64_t)cap * 8, 1ull << 31), rp)) return e;
-        cap = rp.visited_cap;
-        size_t const bytes_per_warp = (size_t)rp.visited_cap * 4 + (size_t)rp.heap_spill_cap * 8;
+        if (char const* e = plan((uint32_t)k, (uint32_t)std::min<uint64_t>(scale, 1u << 30), rp)) return e;
+        maxed = rp.maxed;
+        size_t const bytes_per_warp = (size_t)rp.visited_words_per_warp() * 4 + (size_t)rp.heap_spill_cap * 8;
         size_t max_warps = std::max<size_t>(wpb, ((size_t)2 << 30) / bytes_per_warp / wpb * wpb);
         int rblocks = (int)std::min<size_t>({(size_t)rp.blocks, (failed.size() + wpb - 1) / wpb, max_warps / wpb});
         rblocks = std::max(rblocks, 1);
         size_t rwarps = (size_t)rblocks * wpb;
-        if (char const* e = visited.reserve(rwarps * rp.visited_cap)) return e;
+        if (char const* e = visited.reserve(rwarps * rp.visited_words_per_warp())) return e;
         if (char const* e = heap_spill.reserve(rwarps * rp.heap_spill_cap)) return e;
         if (char const* e = retry_list.reserve(failed.size())) return e;
         CU(cudaMemcpyAsync(retry_list.ptr, failed.data(), failed.size() * 4, cudaMemcpyHostToDevice, s));
         search_args_t r = a;
+        r.heap_smem_cap = rp.heap_smem_cap;
+        r.smem_per_warp = rp.smem_per_warp;
+        r.off_heap = rp.off_heap;
         r.nq = (uint32_t)failed.size();
         r.query_list = retry_list.ptr;
         r.visited = visited.ptr;
         r.visited_cap = rp.visited_cap;
+        r.visited_bitmap_words = rp.visited_bitmap_words;
         r.heap_spill = heap_spill.ptr;
         r.heap_spill_cap = rp.heap_spill_cap;
         CU(cudaMemsetAsync(work_counter.ptr, 0, 8, s));

@@ -22,12 +22,23 @@ cudaError_t search_launch(device_index_t const& ix, search_args_t const& a, int 
 cudaError_t search_occupancy(device_index_t const& ix, int* blocks_per_sm, size_t smem);
 bool search_supported(uint32_t metric, uint32_t scalar);
 int search_warps_per_block();
+bool search_is_staged(device_index_t const& ix);
+int search_stage_slots(device_index_t const& ix);
+bool search_needs_norms(uint32_t metric, uint32_t scalar);
+cudaError_t search_compute_norms(device_index_t const& ix, float* norms, cudaStream_t stream);
+
+/* indexes up to this many slots track `visits` as a per-warp bitmap (512 KB at the limit) */
+constexpr uint64_t BITMAP_MAX_SLOTS = 1ull << 22;
 
 struct launch_plan_t {
     uint32_t ef = 0;
-    uint32_t visited_cap = 0, heap_spill_cap = 0, heap_smem_cap = 0;
+    uint32_t visited_cap = 0, visited_bitmap_words = 0, heap_spill_cap = 0, heap_smem_cap = 0;
+    bool maxed = false; /* growing the scratch any further cannot help */
+    size_t visited_words_per_warp() const { return visited_bitmap_words ? visited_bitmap_words : visited_cap; }
     uint32_t smem_per_warp = 0, off_top_d = 0, off_top_s = 0, off_cand_s = 0, off_cand_d = 0, off_heap = 0;
+    uint32_t off_bars = 0, off_stage = 0, stage_stride = 0, stage_sets = 1;
     int blocks = 0;
+    uint32_t warps_per_sm_target = 0;
     size_t smem_per_block = 0;
     size_t warps() const { return (size_t)blocks * (size_t)search_warps_per_block(); }
 };
@@ -108,6 +119,8 @@ struct frozen_index_t {
     pinned_buffer_t<uint64_t> h_keys;
     pinned_buffer_t<float> h_dists;
     pinned_buffer_t<uint32_t> h_counts, h_computed, h_cycles, h_status;
+    device_buffer_t<unsigned long long> phase_cycles; /* introspection, enabled by usearch_b200_profile_phases */
+    bool profile_phases = false;
     uint64_t kernel_launches = 0;
     float last_kernel_ms = 0.f;
     int sm_count = 0;

@@ -78,6 +78,8 @@ __device__ __forceinline__ float cos_normalize_f32(float ab, float a2, float b2)
 
 struct l2sq_f32_t {
     static constexpr int LPV = 4;
+    static constexpr bool NORMS = false;
+    template <class Q> static __device__ __forceinline__ float finalize(float raw, Q, float) { return raw; }
     struct acc_t { float v[4]; };
     struct qconst_t {};
     static __device__ __forceinline__ void init(acc_t& a) { a.v[0] = a.v[1] = a.v[2] = a.v[3] = 0.f; }
@@ -94,6 +96,8 @@ struct l2sq_f32_t {
 
 struct ip_f32_t {
     static constexpr int LPV = 4;
+    static constexpr bool NORMS = false;
+    template <class Q> static __device__ __forceinline__ float finalize(float raw, Q, float) { return raw; }
     struct acc_t { float v[4]; };
     struct qconst_t {};
     static __device__ __forceinline__ void init(acc_t& a) { a.v[0] = a.v[1] = a.v[2] = a.v[3] = 0.f; }
@@ -109,37 +113,39 @@ struct ip_f32_t {
     static __device__ __forceinline__ qconst_t prepare(uint4 const*, uint32_t, int) { return {}; }
 };
 
+/*  cos f32 reads ||b||^2 from `device_index_t::norms`, computed once at freeze time by the very same
+ *  16-accumulator fma chain (norms_f32_kernel), so the value is bit-identical to what
+ *  simsimd_cos_f32_skylake accumulates in its b2 register (spatial.h:1587-1615) while halving the
+ *  FMAs of the hot loop. The f64 normalisation is deferred: `finish` returns the raw dot product and
+ *  `finalize` is run once per hop, one candidate per lane. */
 struct cos_f32_t {
     static constexpr int LPV = 4;
-    struct acc_t { float ab[4], b2[4]; };
+    static constexpr bool NORMS = true;
+    struct acc_t { float ab[4]; };
     struct qconst_t { float a2; };
-    static __device__ __forceinline__ void init(acc_t& a) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) a.ab[c] = a.b2[c] = 0.f;
-    }
+    static __device__ __forceinline__ void init(acc_t& a) { a.ab[0] = a.ab[1] = a.ab[2] = a.ab[3] = 0.f; }
     static __device__ __forceinline__ void step(acc_t& a, uint4 b, uint4 q) {
-        float bx = __uint_as_float(b.x), by = __uint_as_float(b.y), bz = __uint_as_float(b.z), bw = __uint_as_float(b.w);
-        a.ab[0] = __fmaf_rn(__uint_as_float(q.x), bx, a.ab[0]); a.b2[0] = __fmaf_rn(bx, bx, a.b2[0]);
-        a.ab[1] = __fmaf_rn(__uint_as_float(q.y), by, a.ab[1]); a.b2[1] = __fmaf_rn(by, by, a.b2[1]);
-        a.ab[2] = __fmaf_rn(__uint_as_float(q.z), bz, a.ab[2]); a.b2[2] = __fmaf_rn(bz, bz, a.b2[2]);
-        a.ab[3] = __fmaf_rn(__uint_as_float(q.w), bw, a.ab[3]); a.b2[3] = __fmaf_rn(bw, bw, a.b2[3]);
+        a.ab[0] = __fmaf_rn(__uint_as_float(q.x), __uint_as_float(b.x), a.ab[0]);
+        a.ab[1] = __fmaf_rn(__uint_as_float(q.y), __uint_as_float(b.y), a.ab[1]);
+        a.ab[2] = __fmaf_rn(__uint_as_float(q.z), __uint_as_float(b.z), a.ab[2]);
+        a.ab[3] = __fmaf_rn(__uint_as_float(q.w), __uint_as_float(b.w), a.ab[3]);
     }
-    static __device__ __forceinline__ float finish(acc_t const& a, qconst_t qc) {
-        float ab = reduce16_f32(a.ab);
-        float b2 = reduce16_f32(a.b2);
-        return cos_normalize_f64(ab, qc.a2, b2);
-    }
-    /* a2 = dot(q, q) in the same 16-accumulator order; every 4-lane group computes the same value */
-    static __device__ __forceinline__ qconst_t prepare(uint4 const* q4, uint32_t chunks16, int lane) {
+    static __device__ __forceinline__ float finish(acc_t const& a, qconst_t) { return reduce16_f32(a.ab); }
+    static __device__ __forceinline__ float finalize(float ab, qconst_t qc, float b2) { return cos_normalize_f64(ab, qc.a2, b2); }
+    /* dot(v, v) in the 16-accumulator order; every 4-lane group computes the same value */
+    static __device__ __forceinline__ float self_dot(uint4 const* v4, uint32_t chunks16, int lane) {
         float v[4] = {0.f, 0.f, 0.f, 0.f};
         for (uint32_t j = lane & 3; j < chunks16; j += 4) {
-            uint4 q = q4[j];
+            uint4 q = v4[j];
             v[0] = __fmaf_rn(__uint_as_float(q.x), __uint_as_float(q.x), v[0]);
             v[1] = __fmaf_rn(__uint_as_float(q.y), __uint_as_float(q.y), v[1]);
             v[2] = __fmaf_rn(__uint_as_float(q.z), __uint_as_float(q.z), v[2]);
             v[3] = __fmaf_rn(__uint_as_float(q.w), __uint_as_float(q.w), v[3]);
         }
-        return {reduce16_f32(v)};
+        return reduce16_f32(v);
+    }
+    static __device__ __forceinline__ qconst_t prepare(uint4 const* q4, uint32_t chunks16, int lane) {
+        return {self_dot(q4, chunks16, lane)};
     }
 };
 
@@ -147,6 +153,8 @@ struct cos_f32_t {
 
 template <int LPV_> struct ip_i8_t {
     static constexpr int LPV = LPV_;
+    static constexpr bool NORMS = false;
+    template <class Q> static __device__ __forceinline__ float finalize(float raw, Q, float) { return raw; }
     struct acc_t { int ab; };
     struct qconst_t {};
     static __device__ __forceinline__ void init(acc_t& a) { a.ab = 0; }
@@ -165,6 +173,8 @@ template <int LPV_> struct ip_i8_t {
 
 template <int LPV_> struct l2sq_i8_t {
     static constexpr int LPV = LPV_;
+    static constexpr bool NORMS = false;
+    template <class Q> static __device__ __forceinline__ float finalize(float raw, Q, float) { return raw; }
     struct acc_t { int d2; };
     struct qconst_t {};
     static __device__ __forceinline__ void init(acc_t& a) { a.d2 = 0; }
@@ -186,6 +196,8 @@ template <int LPV_> struct l2sq_i8_t {
 
 template <int LPV_> struct cos_i8_t {
     static constexpr int LPV = LPV_;
+    static constexpr bool NORMS = false;
+    template <class Q> static __device__ __forceinline__ float finalize(float raw, Q, float) { return raw; }
     struct acc_t { int ab, b2; };
     struct qconst_t { int a2; };
     static __device__ __forceinline__ void init(acc_t& a) { a.ab = a.b2 = 0; }
@@ -214,6 +226,8 @@ template <int LPV_> struct cos_i8_t {
 
 template <int LPV_> struct hamming_b1_t {
     static constexpr int LPV = LPV_;
+    static constexpr bool NORMS = false;
+    template <class Q> static __device__ __forceinline__ float finalize(float raw, Q, float) { return raw; }
     struct acc_t { int d; };
     struct qconst_t {};
     static __device__ __forceinline__ void init(acc_t& a) { a.d = 0; }
@@ -226,6 +240,8 @@ template <int LPV_> struct hamming_b1_t {
 
 template <int LPV_> struct tanimoto_b1_t {
     static constexpr int LPV = LPV_;
+    static constexpr bool NORMS = false;
+    template <class Q> static __device__ __forceinline__ float finalize(float raw, Q, float) { return raw; }
     struct acc_t { int and_, or_; };
     struct qconst_t {};
     static __device__ __forceinline__ void init(acc_t& a) { a.and_ = a.or_ = 0; }
@@ -242,6 +258,8 @@ template <int LPV_> struct tanimoto_b1_t {
 
 template <int LPV_> struct sorensen_b1_t {
     static constexpr int LPV = LPV_;
+    static constexpr bool NORMS = false;
+    template <class Q> static __device__ __forceinline__ float finalize(float raw, Q, float) { return raw; }
     struct acc_t { int and_, any_; };
     struct qconst_t {};
     static __device__ __forceinline__ void init(acc_t& a) { a.and_ = a.any_ = 0; }

@@ -12,15 +12,20 @@
  *  so the returned labels are bit-identical to the CPU search at the same ef, ties included.
  *
  *  How the work is laid out on the GPU is new:
- *    - a persistent grid (a multiple of the SM count) pulls query ids from one atomic counter;
+ *    - a persistent grid (a multiple of the SM count, one warp per CTA) pulls query ids from one
+ *      atomic counter;
  *    - the per-query state lives in shared memory: the query itself (read ~D times), `top`
  *      (sorted, maintained by the whole warp with ballots), the head of the `next` heap (its
  *      deep levels spill to a per-warp slab in HBM), the hop's candidate list;
  *    - `visits` is an open-addressing table in a per-warp slab of HBM driven with atomicCAS at
  *      L2, so that the 32 lanes test-and-set a whole neighbour list at once;
- *    - the M0 neighbour distances of a hop are computed together: LPV lanes per stored vector,
- *      128-bit streaming loads, 8 loads in flight per lane; only the accept/insert replay that
- *      follows is sequential, exactly as the reference's inner loop is.
+ *    - the neighbour vectors of a hop are fetched together. STAGED kernels (vectors >= 256 B) issue
+ *      one TMA bulk copy (cp.async.bulk, UBLKCP) per candidate vector into a shared-memory slot and
+ *      wait on its mbarrier: eight whole vectors are in flight per warp without holding a single
+ *      register, and LPV lanes then reduce each slot in the reference's summation order. DIRECT
+ *      kernels (short vectors: binary codes) stream 16-byte chunks through registers instead;
+ *    - only the accept/insert replay that follows is sequential, as the reference's inner loop is,
+ *      and it only visits the candidates that can still pass the radius test.
  */
 #include <cuda_runtime.h>
 
@@ -29,61 +34,193 @@
 
 namespace usearch_b200 {
 
-constexpr int WARPS_PER_BLOCK = 4;
-constexpr int THREADS = WARPS_PER_BLOCK * 32;
+constexpr int THREADS = 32; /* one warp per CTA: warps never synchronise with each other */
 constexpr int LOADS_IN_FLIGHT = 8;
 
 __device__ __forceinline__ uint32_t hash_slot(uint32_t s) { return s * 0x9E3779B1u; }
 
+/* ---- TMA bulk copy + mbarrier (PTX ISA: cp.async.bulk, mbarrier.*) ---------------------------- */
+
+__device__ __forceinline__ uint32_t smem_u32(void const* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, void const* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
 /* ---- `next`: binary max-heap on -distance, stored as +distance with reversed compares ------ */
 
+/*
+ *  Same tree, same sift rules as max_heap_gt (index.hpp:664-835), therefore the same pop order on
+ *  ties. Storage is 1-based: logical element i lives at physical index i+1, so the two children of
+ *  physical node p are the ADJACENT pair (2p, 2p+1) — one 16-byte load fetches both. Physical
+ *  indices below `smem_cap` are in shared memory, deeper ones spill to the warp's slab in HBM.
+ */
 struct heap_t {
-    cand_t* smem;
+    uint32_t smem_addr; /* shared-window address of physical index 0 (explicit ld/st.shared: never generic) */
     cand_t* spill;
-    uint32_t smem_cap;
-    __device__ __forceinline__ cand_t get(uint32_t i) const { return i < smem_cap ? smem[i] : spill[i - smem_cap]; }
-    __device__ __forceinline__ void put(uint32_t i, cand_t c) const {
-        if (i < smem_cap) smem[i] = c;
-        else spill[i - smem_cap] = c;
+    uint32_t smem_cap; /* even */
+    static __device__ __forceinline__ cand_t lds(uint32_t addr) {
+        cand_t c;
+        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=f"(c.d), "=r"(c.s) : "r"(addr));
+        return c;
     }
-    /* max_heap_gt::insert_reserved + shift_up (index.hpp:764-770, :808-811). `size` is the size before. */
-    __device__ void push(uint32_t size, cand_t c) const {
-        uint32_t i = size;
-        while (i) {
-            uint32_t p = (i - 1) >> 1;
-            cand_t pe = get(p);
-            if (!(pe.d > c.d)) break; /* less(parent, child) <=> -parent.d < -child.d */
-            put(i, pe);
-            i = p;
-        }
-        put(i, c);
+    static __device__ __forceinline__ void sts(uint32_t addr, cand_t c) {
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "f"(c.d), "r"(c.s) : "memory");
     }
-    /* max_heap_gt::pop + shift_down (index.hpp:786-794, :819-834). `size` is the size before (>0). */
-    __device__ void pop(uint32_t size) const {
-        uint32_t n = size - 1;
+    __device__ __forceinline__ cand_t get(uint32_t p) const {
+        if (p < smem_cap) return lds(smem_addr + 8u * p);
+        return spill[p - smem_cap];
+    }
+    __device__ __forceinline__ void put(uint32_t p, cand_t c) const {
+        if (p < smem_cap) sts(smem_addr + 8u * p, c);
+        else spill[p - smem_cap] = c;
+    }
+    __device__ __forceinline__ cand_t root() const { return lds(smem_addr + 8u); }
+    __device__ __forceinline__ void set_root(cand_t c) const { sts(smem_addr + 8u, c); }
+
+    /* max_heap_gt::insert_reserved + shift_up (index.hpp:764-770, :808-811), by the whole warp: the
+     * ancestors of the new leaf are known up front (p>>1, p>>2, ...), lane l fetches the one at level l;
+     * the first ancestor that is NOT `less` than the element (parent.d <= c.d) stops the climb — the
+     * sequential loop stops at exactly that ancestor — and everything below it moves down one step.
+     * `size` is the number of elements before the push. */
+    __device__ __forceinline__ void push(uint32_t size, cand_t c, int lane) const {
+        uint32_t const p = size + 1;
+        uint32_t const depth = 31u - (uint32_t)__clz(p);
+        cand_t e{0.f, 0u};
+        if ((uint32_t)lane < depth) e = get(p >> (lane + 1));
+        uint32_t const stops = __ballot_sync(0xffffffffu, (uint32_t)lane < depth && !(e.d > c.d));
+        uint32_t const stop = stops ? (uint32_t)__ffs(stops) - 1u : depth;
+        if ((uint32_t)lane < stop) put(p >> lane, e);
+        if (lane == 0) put(p >> stop, c);
+        __syncwarp();
+    }
+
+    /* max_heap_gt::pop + shift_down (index.hpp:786-794, :819-834), lane 0 only. `size` is the size
+     * before the pop (> 0). The root has already been read by the caller. */
+    __device__ __forceinline__ void pop(uint32_t size) const {
+        uint32_t const n = size - 1; /* elements that remain: physical 1..n */
         if (n == 0) return;
-        cand_t last = get(n);
-        uint32_t i = 0;
+        cand_t const last = get(size);
+        uint32_t p = 1;
         for (;;) {
-            uint32_t l = 2 * i + 1, r = l + 1, best_i = i;
-            float best = last.d;
+            uint32_t const l = 2 * p, r = l + 1;
+            if (l > n) break;
             cand_t le, re;
-            if (l < n) { le = get(l); if (best > le.d) { best_i = l; best = le.d; } }
-            if (r < n) { re = get(r); if (best > re.d) { best_i = r; } }
-            if (best_i == i) break;
-            put(i, best_i == l ? le : re);
-            i = best_i;
+            if (r < smem_cap) { /* both children in shared memory: one 16-byte load */
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(le.d), "=r"(le.s), "=f"(re.d), "=r"(re.s)
+                             : "r"(smem_addr + 8u * l));
+            } else {
+                le = get(l);
+                re = r <= n ? get(r) : le;
+            }
+            uint32_t best_i = p;
+            float best = last.d;
+            if (best > le.d) { best_i = l; best = le.d; }
+            if (r <= n && best > re.d) best_i = r;
+            if (best_i == p) break;
+            put(p, best_i == l ? le : re);
+            p = best_i;
         }
-        put(i, last);
+        put(p, last);
+    }
+
+    /*
+     *  The same pop by the whole warp, for heaps whose internal nodes all sit in shared memory
+     *  (size <= 2*32*8 = 512 and size <= smem_cap). shift_down follows, from the root, the child chosen by
+     *  `less`: right iff (right exists && right.d < left.d), else left — a choice that does not depend on
+     *  the element being sifted — and stops at the first level where the sifted element is not worse
+     *  (last.d > child.d fails); see index.hpp:819-834: `best` starts as last.d, moves to le.d if
+     *  last.d > le.d, then to re.d if best > re.d, which is exactly "last.d > min-child.d, ties to the left".
+     *    1. every lane evaluates the choice bit of 8 internal nodes: one 16-byte load each, 8 ballots;
+     *    2. all lanes walk the <= 9 levels on those bits in registers (no memory on the critical path);
+     *    3. lane k fetches the path node of level k, a ballot finds the stop level, the path shifts up.
+     *  Returns false (nothing done) when the heap is too large: the caller falls back to `pop`.
+     */
+    __device__ __forceinline__ bool pop_warp(uint32_t size, int lane) const {
+        uint32_t const n = size - 1;
+        if (n == 0) return true;
+        if (size > 512u || size >= smem_cap) return false;
+        cand_t const last = lds(smem_addr + 8u * size);
+        uint32_t const internal = n >> 1; /* nodes 1..internal have at least a left child */
+        uint32_t w[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            w[r] = 0u;
+            if ((uint32_t)(r * 32) <= internal) {
+                uint32_t const p = (uint32_t)(r * 32 + lane);
+                bool right = false;
+                if (p >= 1u && 2u * p + 1u <= n) {
+                    cand_t le, re;
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                 : "=f"(le.d), "=r"(le.s), "=f"(re.d), "=r"(re.s)
+                                 : "r"(smem_addr + 16u * p));
+                    right = re.d < le.d;
+                }
+                w[r] = __ballot_sync(0xffffffffu, right);
+            }
+        }
+        /* walk: level k node p -> 2p + choice(p); the word holding choice(p) is static per level */
+        uint32_t p = 1, mine = 1, parent = 1, depth = 0;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            if (2u * p <= n) {
+                uint32_t word;
+                if (k <= 4) word = w[0];
+                else if (k == 5) word = w[1];
+                else if (k == 6) word = (p & 32u) ? w[3] : w[2];
+                else if (k == 7) word = (p & 64u) ? ((p & 32u) ? w[7] : w[6]) : ((p & 32u) ? w[5] : w[4]);
+                else word = 0u; /* level-8 nodes (256..511) have no children when size <= 512 */
+                uint32_t const child = 2u * p + ((word >> (p & 31u)) & 1u);
+                if (lane == k + 1) { mine = child; parent = p; }
+                p = child;
+                depth = (uint32_t)k + 1u;
+            }
+        }
+        /* lane k (1..depth) owns path node p_k and its parent p_{k-1} */
+        cand_t e{0.f, 0u};
+        bool const on_path = lane >= 1 && (uint32_t)lane <= depth;
+        if (on_path) e = lds(smem_addr + 8u * mine);
+        uint32_t const stays = __ballot_sync(0xffffffffu, on_path && !(last.d > e.d));
+        uint32_t const moves = stays ? (uint32_t)__ffs(stays) - 2u : depth; /* levels 1..moves shift up */
+        if (on_path && (uint32_t)lane <= moves) sts(smem_addr + 8u * parent, e);
+        /* `last` lands on path node p_moves (the root when nothing moved) */
+        uint32_t const landing = __shfl_sync(0xffffffffu, mine, (int)moves);
+        if (lane == 0) sts(smem_addr + 8u * (moves ? landing : 1u), last);
+        return true;
     }
 };
 
 /* ---- `top`: ascending sorted array, maintained by the whole warp ---------------------------- */
 
-/* sorted_buffer_gt::insert(element, limit) (index.hpp:928-939). Uniform across the warp. */
+/* sorted_buffer_gt::insert(element, limit) (index.hpp:928-939). Uniform across the warp.
+ * Lane l owns elements l, l+32, ...: every element is loaded once (the same loads feed the
+ * lower_bound ballots), one barrier, then every element at or after the insertion point is
+ * stored one place to the right. */
 __device__ __forceinline__ void top_insert(float* td, uint32_t* ts, uint32_t& size, uint32_t limit, float d, uint32_t s,
                                            int lane) {
-    uint32_t pos = 0; /* lower_bound: number of stored distances strictly below d */
+    uint32_t pos = 0;
     for (uint32_t b = 0; b < size; b += 32) {
         uint32_t i = b + lane;
         bool lt = i < size && td[i] < d;
@@ -91,7 +228,7 @@ __device__ __forceinline__ void top_insert(float* td, uint32_t* ts, uint32_t& si
     }
     if (pos == limit) return;
     bool full = size == limit;
-    uint32_t hi = size - (full ? 1u : 0u); /* [pos, hi) shifts one to the right */
+    uint32_t hi = size - (full ? 1u : 0u);
     if (hi > pos) {
         for (int b = (int)((hi - 1) & ~31u); b >= (int)(pos & ~31u); b -= 32) {
             uint32_t i = (uint32_t)b + lane;
@@ -109,18 +246,78 @@ __device__ __forceinline__ void top_insert(float* td, uint32_t* ts, uint32_t& si
     __syncwarp();
 }
 
+/*
+ *  Register-resident `top` for ef <= 256: lane l holds elements l, l+32, ... (TOP_E chunks). The
+ *  same sorted_buffer_gt::insert semantics, but the right-shift is done with shuffles: element i
+ *  receives element i-1, which lives in the neighbouring lane (or in lane 31 of the previous chunk).
+ */
+constexpr int TOP_E = 8;
+
+__device__ __forceinline__ void top_insert_reg(float (&td)[TOP_E], uint32_t (&ts)[TOP_E], uint32_t& size, uint32_t limit,
+                                               float d, uint32_t s, int lane) {
+    uint32_t mine = 0; /* lower_bound: number of stored distances strictly below d */
+#pragma unroll
+    for (int c = 0; c < TOP_E; ++c) mine += ((uint32_t)(c * 32 + lane) < size && td[c] < d) ? 1u : 0u;
+    uint32_t const pos = __reduce_add_sync(0xffffffffu, mine);
+    if (pos == limit) return;
+    bool const full = size == limit;
+    uint32_t const hi = size - (full ? 1u : 0u); /* old [pos, hi) becomes new (pos, hi] */
+#pragma unroll
+    for (int c = TOP_E - 1; c >= 0; --c) {
+        if (c * 32 <= (int)hi && (c + 1) * 32 > (int)pos) { /* chunk intersects [pos, hi] */
+            float pd = __shfl_up_sync(0xffffffffu, td[c], 1);
+            uint32_t ps = __shfl_up_sync(0xffffffffu, ts[c], 1);
+            if (c > 0) {
+                float cd = __shfl_sync(0xffffffffu, td[c - 1 < 0 ? 0 : c - 1], 31);
+                uint32_t cs = __shfl_sync(0xffffffffu, ts[c - 1 < 0 ? 0 : c - 1], 31);
+                if (lane == 0) { pd = cd; ps = cs; }
+            }
+            uint32_t const i = (uint32_t)(c * 32 + lane);
+            if (i > pos && i <= hi) { td[c] = pd; ts[c] = ps; }
+            else if (i == pos) { td[c] = d; ts[c] = s; }
+        }
+    }
+    size += full ? 0u : 1u;
+}
+
+/* distance of the last (worst) element: sorted_buffer_gt::top() (index.hpp:891) */
+__device__ __forceinline__ float top_back_reg(float const (&td)[TOP_E], uint32_t size) {
+    uint32_t const i = size - 1, cc = i >> 5;
+    float sel = 0.f;
+#pragma unroll
+    for (int c = 0; c < TOP_E; ++c)
+        if ((uint32_t)c == cc) sel = td[c];
+    return __shfl_sync(0xffffffffu, sel, (int)(i & 31));
+}
+
+/* ---- per-warp view of shared memory and scratch ---------------------------------------------- */
+
+struct warp_ctx_t {
+    uint4* q4;
+    float* top_d;
+    uint32_t* top_s;
+    uint32_t* cand_s;
+    float* cand_d;
+    uint8_t* stage;      /* STAGED: VPP slots of stage_stride bytes */
+    uint32_t stage_addr; /* shared-window address of `stage` */
+    uint32_t bars_addr;  /* shared-window address of the VPP mbarriers */
+    uint32_t phase;      /* one parity bit per slot, uniform across the warp */
+    uint32_t t_wait;     /* introspection: cycles spent waiting for staged vectors */
+};
+
 /* ---- distances of a whole candidate list ---------------------------------------------------- */
 
+/* DIRECT: 16-byte chunks straight from HBM into registers, LOADS_IN_FLIGHT per lane. */
 template <class M>
-__device__ __noinline__ void measure_list(device_index_t const& ix, uint4 const* q4, typename M::qconst_t qc,
-                                             uint32_t const* cand_s, float* cand_d, uint32_t ncand, int lane) {
+__device__ __noinline__ void measure_direct(device_index_t const& ix, warp_ctx_t& w, typename M::qconst_t qc,
+                                               uint32_t ncand, int lane) {
     constexpr int LPV = M::LPV, VPP = 32 / LPV;
     int const g = lane / LPV, sub = lane % LPV;
     uint32_t const chunks = ix.chunks16;
     for (uint32_t base = 0; base < ncand; base += VPP) {
         uint32_t c = base + g;
         bool act = c < ncand;
-        uint32_t slot = act ? cand_s[c] : 0u;
+        uint32_t slot = act ? w.cand_s[c] : 0u;
         uint4 const* v = reinterpret_cast<uint4 const*>(ix.vectors + (size_t)slot * ix.vec_stride);
         typename M::acc_t acc;
         M::init(acc);
@@ -134,29 +331,127 @@ __device__ __noinline__ void measure_list(device_index_t const& ix, uint4 const*
 #pragma unroll
             for (int u = 0; u < LOADS_IN_FLIGHT; ++u) {
                 uint32_t j = j0 + u * LPV;
-                if (act && j < chunks) M::step(acc, r[u], q4[j]);
+                if (act && j < chunks) M::step(acc, r[u], w.q4[j]);
             }
         }
         float d = M::finish(acc, qc); /* warp-wide shuffles inside: executed by every lane */
-        if (act && sub == 0) cand_d[c] = d;
+        if (act && sub == 0) w.cand_d[c] = d;
     }
     __syncwarp();
 }
 
+/* STAGED: one TMA bulk copy per candidate vector into a shared-memory slot, then LPV lanes per slot. */
+template <class M>
+__device__ __forceinline__ void measure_staged(device_index_t const& ix, search_args_t const& a, warp_ctx_t& w,
+                                               typename M::qconst_t qc, uint32_t ncand, int lane) {
+    constexpr int LPV = M::LPV, VPP = 32 / LPV;
+    int const g = lane / LPV, sub = lane % LPV;
+    uint32_t const chunks = ix.chunks16, bytes = (uint32_t)ix.vec_stride;
+    uint32_t const nsets = a.stage_sets; /* 1: fetch-then-reduce; 2: the next pass lands while this one is reduced */
+    uint32_t const npass = (ncand + VPP - 1) / VPP;
+    /* pass p = candidates [p*VPP, p*VPP+VPP) -> slot set p % nsets; lane l < cnt issues the copy of slot l */
+    auto issue = [&](uint32_t p) {
+        uint32_t const base = p * VPP, cnt = min((uint32_t)VPP, ncand - base);
+        if (lane < (int)cnt) {
+            uint32_t const slot = w.cand_s[base + lane], sl = (p % nsets) * VPP + lane;
+            uint32_t const bar = w.bars_addr + 8u * sl;
+            mbar_expect_tx(bar, bytes);
+            bulk_copy_g2s(w.stage_addr + sl * a.stage_stride, ix.vectors + (size_t)slot * ix.vec_stride, bytes, bar);
+        }
+    };
+    issue(0);
+    if (nsets > 1 && npass > 1) issue(1);
+    for (uint32_t p = 0; p < npass; ++p) {
+        uint32_t const base = p * VPP, cnt = min((uint32_t)VPP, ncand - base);
+        uint32_t const sl = (p % nsets) * VPP + g;
+        uint4 const* buf = reinterpret_cast<uint4 const*>(w.stage + (size_t)sl * a.stage_stride);
+        bool const act = (uint32_t)g < cnt;
+        typename M::acc_t acc;
+        M::init(acc);
+        if (a.phase_cycles) { /* introspection only: attribute the wait for the slowest slot to `vector_wait` */
+            long long t = clock64();
+            if (act) mbar_wait(w.bars_addr + 8u * sl, (w.phase >> sl) & 1u);
+            __syncwarp();
+            w.t_wait += (uint32_t)(clock64() - t);
+        }
+        if (act) {
+            if (!a.phase_cycles) mbar_wait(w.bars_addr + 8u * sl, (w.phase >> sl) & 1u);
+            /* 4 steps per iteration, the next iteration's 8 shared-memory loads issued before this one's
+             * math: with one warp per scheduler nothing else hides the LDS latency */
+            uint32_t j = sub;
+            if (j + 3 * LPV < chunks) {
+                uint4 b0 = buf[j], b1 = buf[j + LPV], b2 = buf[j + 2 * LPV], b3 = buf[j + 3 * LPV];
+                uint4 q0 = w.q4[j], q1 = w.q4[j + LPV], q2 = w.q4[j + 2 * LPV], q3 = w.q4[j + 3 * LPV];
+                j += 4 * LPV;
+                for (; j + 3 * LPV < chunks; j += 4 * LPV) {
+                    uint4 nb0 = buf[j], nb1 = buf[j + LPV], nb2 = buf[j + 2 * LPV], nb3 = buf[j + 3 * LPV];
+                    uint4 nq0 = w.q4[j], nq1 = w.q4[j + LPV], nq2 = w.q4[j + 2 * LPV], nq3 = w.q4[j + 3 * LPV];
+                    M::step(acc, b0, q0);
+                    M::step(acc, b1, q1);
+                    M::step(acc, b2, q2);
+                    M::step(acc, b3, q3);
+                    b0 = nb0; b1 = nb1; b2 = nb2; b3 = nb3;
+                    q0 = nq0; q1 = nq1; q2 = nq2; q3 = nq3;
+                }
+                M::step(acc, b0, q0);
+                M::step(acc, b1, q1);
+                M::step(acc, b2, q2);
+                M::step(acc, b3, q3);
+            }
+            for (; j < chunks; j += LPV) M::step(acc, buf[j], w.q4[j]);
+        }
+        float d = M::finish(acc, qc);
+        if (act && sub == 0) w.cand_d[base + g] = d;
+        w.phase ^= ((1u << cnt) - 1u) << ((p % nsets) * VPP);
+        __syncwarp(); /* every lane is done with this set before it is refilled */
+        if (p + nsets < npass) issue(p + nsets);
+    }
+}
+
+template <class M, bool STAGED>
+__device__ __forceinline__ void measure_list(device_index_t const& ix, search_args_t const& a, warp_ctx_t& w,
+                                             typename M::qconst_t qc, uint32_t ncand, int lane) {
+    float n0 = 0.f, n1 = 0.f;
+    if constexpr (M::NORMS) { /* requested now, consumed after the last pass */
+        if ((uint32_t)lane < ncand) n0 = __ldg(ix.norms + w.cand_s[lane]);
+        if ((uint32_t)lane + 32 < ncand) n1 = __ldg(ix.norms + w.cand_s[lane + 32]);
+    }
+    if constexpr (STAGED) measure_staged<M>(ix, a, w, qc, ncand, lane);
+    else measure_direct<M>(ix, w, qc, ncand, lane);
+    if constexpr (M::NORMS) { /* one candidate per lane: a single f64 normalisation sequence per hop */
+        if ((uint32_t)lane < ncand) w.cand_d[lane] = M::finalize(w.cand_d[lane], qc, n0);
+        if ((uint32_t)lane + 32 < ncand) w.cand_d[lane + 32] = M::finalize(w.cand_d[lane + 32], qc, n1);
+        for (uint32_t c = 64 + lane; c < ncand; c += 32) w.cand_d[c] = M::finalize(w.cand_d[c], qc, __ldg(ix.norms + w.cand_s[c]));
+        __syncwarp();
+    }
+}
+
 /* ---- one query ------------------------------------------------------------------------------ */
 
-template <class M>
-__device__ void search_one(device_index_t const& ix, search_args_t const& a, uint32_t qi, uint8_t* my_smem,
-                           uint32_t* visited, cand_t* spill, int lane) {
-    uint4* q4 = reinterpret_cast<uint4*>(my_smem);
-    float* top_d = reinterpret_cast<float*>(my_smem + a.off_top_d);
-    uint32_t* top_s = reinterpret_cast<uint32_t*>(my_smem + a.off_top_s);
-    uint32_t* cand_s = reinterpret_cast<uint32_t*>(my_smem + a.off_cand_s);
-    float* cand_d = reinterpret_cast<float*>(my_smem + a.off_cand_d);
-    heap_t heap{reinterpret_cast<cand_t*>(my_smem + a.off_heap), spill, a.heap_smem_cap};
-
+template <class M, bool STAGED>
+__device__ __forceinline__ void search_one(device_index_t const& ix, search_args_t const& a, uint32_t qi, warp_ctx_t& w,
+                                           heap_t const& heap, uint32_t* visited, int lane) {
     uint32_t const k = a.k, ef = a.ef;
     uint32_t top_size = 0, heap_size = 0, computed = 0, cycles = 0, status = STATUS_OK;
+    bool const prof = a.phase_cycles != nullptr;
+    uint32_t pc0 = 0, pc1 = 0, pc2 = 0, pc4 = 0, pc5 = 0, n_push = 0, max_heap = 0;
+    long long tp = prof ? clock64() : 0;
+    w.t_wait = 0;
+#define PHASE(acc)                                  \
+    if (prof) {                                     \
+        long long now_ = clock64();                 \
+        acc += (uint32_t)(now_ - tp);               \
+        tp = now_;                                  \
+    }
+    float* const top_d = w.top_d; /* shared-memory `top`: only for ef > 32*TOP_E */
+    uint32_t* const top_s = w.top_s;
+    bool const topreg = ef <= 32u * TOP_E;
+    float rtd[TOP_E];
+    uint32_t rts[TOP_E];
+#pragma unroll
+    for (int c = 0; c < TOP_E; ++c) { rtd[c] = 0.f; rts[c] = 0u; }
+    uint32_t* const cand_s = w.cand_s;
+    float* const cand_d = w.cand_d;
 
     if (ix.n != 0 && k != 0) {
         /* stage the query, zero-padded to whole 16-byte chunks */
@@ -165,21 +460,24 @@ __device__ void search_one(device_index_t const& ix, search_args_t const& a, uin
             uint32_t const bpv = ix.bytes_per_vector;
             bool wide = ((reinterpret_cast<size_t>(src) | a.query_stride) & 15) == 0 && a.query_stride >= (uint64_t)ix.chunks16 * 16;
             if (wide) {
-                for (uint32_t j = lane; j < ix.chunks16; j += 32) q4[j] = reinterpret_cast<uint4 const*>(src)[j];
+                for (uint32_t j = lane; j < ix.chunks16; j += 32) w.q4[j] = reinterpret_cast<uint4 const*>(src)[j];
             } else {
-                uint8_t* dst = reinterpret_cast<uint8_t*>(q4);
+                uint8_t* dst = reinterpret_cast<uint8_t*>(w.q4);
                 for (uint32_t b = lane; b < ix.chunks16 * 16; b += 32) dst[b] = b < bpv ? src[b] : (uint8_t)0;
             }
         }
         /* visits.clear() */
+        bool const bitmap = a.visited_bitmap_words != 0;
         {
-            uint4 const ones = make_uint4(EMPTY_SLOT, EMPTY_SLOT, EMPTY_SLOT, EMPTY_SLOT);
+            uint32_t const fill = bitmap ? 0u : EMPTY_SLOT;
+            uint4 const word = make_uint4(fill, fill, fill, fill);
             uint4* v4 = reinterpret_cast<uint4*>(visited);
-            for (uint32_t j = lane; j < a.visited_cap / 4; j += 32) v4[j] = ones;
+            uint32_t const n4 = (bitmap ? a.visited_bitmap_words : a.visited_cap) / 4;
+            for (uint32_t j = lane; j < n4; j += 32) v4[j] = word;
         }
         __threadfence_block();
         __syncwarp();
-        typename M::qconst_t qc = M::prepare(q4, ix.chunks16, lane);
+        typename M::qconst_t qc = M::prepare(w.q4, ix.chunks16, lane);
         uint32_t const vmask = a.visited_cap - 1;
         uint32_t visited_count = 0;
 
@@ -187,7 +485,7 @@ __device__ void search_one(device_index_t const& ix, search_args_t const& a, uin
         uint32_t closest = ix.entry_slot;
         if (lane == 0) cand_s[0] = closest;
         __syncwarp();
-        measure_list<M>(ix, q4, qc, cand_s, cand_d, 1, lane);
+        measure_list<M, STAGED>(ix, a, w, qc, 1, lane);
         computed += 1;
         float closest_d = cand_d[0];
         __syncwarp();
@@ -207,18 +505,17 @@ __device__ void search_one(device_index_t const& ix, search_args_t const& a, uin
                     n += __popc(bal);
                 }
                 __syncwarp();
-                measure_list<M>(ix, q4, qc, cand_s, cand_d, n, lane);
+                measure_list<M, STAGED>(ix, a, w, qc, n, lane);
                 computed += n;
                 /* sequential `if (d < closest_d)` scan == first occurrence of the strict minimum */
                 for (uint32_t b = 0; b < n; b += 32) {
                     uint32_t i = b + lane;
                     float d = i < n ? cand_d[i] : 0.f;
                     bool better = i < n && d < closest_d;
-                    /* warp argmin with first-index tie-break */
                     float best = better ? d : __int_as_float(0x7f800000);
                     uint32_t best_i = better ? i : 0xFFFFFFFFu;
 #pragma unroll
-                    for (int o = 16; o; o >>= 1) {
+                    for (int o = 16; o; o >>= 1) { /* warp argmin with first-index tie-break */
                         float od = __shfl_xor_sync(0xffffffffu, best, o);
                         uint32_t oi = __shfl_xor_sync(0xffffffffu, best_i, o);
                         if (oi != 0xFFFFFFFFu && (best_i == 0xFFFFFFFFu || od < best || (od == best && oi < best_i))) {
@@ -240,84 +537,151 @@ __device__ void search_one(device_index_t const& ix, search_args_t const& a, uin
         /* ---- search_to_find_in_base_ (index.hpp:4175-4246) ---- */
         if (lane == 0) cand_s[0] = closest;
         __syncwarp();
-        measure_list<M>(ix, q4, qc, cand_s, cand_d, 1, lane);
+        measure_list<M, STAGED>(ix, a, w, qc, 1, lane);
         computed += 1;
         float radius = cand_d[0];
         __syncwarp();
         if (lane == 0) {
-            heap.put(0, cand_t{radius, closest});
-            atomicCAS(&visited[hash_slot(closest) & vmask], EMPTY_SLOT, closest);
+            heap.set_root(cand_t{radius, closest});
+            if (bitmap) atomicOr(&visited[closest >> 5], 1u << (closest & 31));
+            else atomicCAS(&visited[hash_slot(closest) & vmask], EMPTY_SLOT, closest);
         }
         heap_size = 1;
         visited_count = 1;
+        uint32_t pre_node = EMPTY_SLOT, pre_s0 = EMPTY_SLOT, pre_s1 = EMPTY_SLOT; /* speculative row prefetch */
+        PHASE(pc0)
         {
             bool allowed = !ix.deleted_bits || !((ix.deleted_bits[closest >> 5] >> (closest & 31)) & 1u);
             if (allowed) {
-                if (lane == 0) { top_d[0] = radius; top_s[0] = closest; }
+                if (topreg) {
+                    if (lane == 0) { rtd[0] = radius; rts[0] = closest; }
+                } else if (lane == 0) { top_d[0] = radius; top_s[0] = closest; }
                 top_size = 1;
             }
         }
         __syncwarp();
 
         while (heap_size) {
-            cand_t cur = heap.smem[0];
+            cand_t cur = heap.root();
             if (cur.d > radius && top_size == ef) break;
+            /* the neighbour row is addressed by the root alone: fetch it while lane 0 sifts the heap */
+            uint32_t const* row = ix.nbr0 + (size_t)cur.s * ix.m0_stride;
+            uint32_t s0, s1;
+            if (cur.s == pre_node) { /* the row was prefetched during the previous hop */
+                s0 = pre_s0;
+                s1 = pre_s1;
+            } else {
+                s0 = lane < (int)ix.m0 ? __ldg(row + lane) : EMPTY_SLOT;
+                s1 = lane + 32 < (int)ix.m0 ? __ldg(row + lane + 32) : EMPTY_SLOT;
+            }
             __syncwarp(); /* every lane holds `cur` before lane 0 rearranges the heap */
-            if (lane == 0) heap.pop(heap_size);
+            /* BITMAP visits: one atomicOr per neighbour, all in flight together (the frozen lists hold no
+             * duplicates and no self-links: those can never be `fresh`, freeze drops them). They are issued
+             * BEFORE the pop so that lane 0 sifts the heap while the atomics make their round trip to L2. */
+            uint32_t o0 = 0xFFFFFFFFu, o1 = 0xFFFFFFFFu;
+            if (bitmap) {
+                if (s0 != EMPTY_SLOT) o0 = atomicOr(&visited[s0 >> 5], 1u << (s0 & 31));
+                if (s1 != EMPTY_SLOT) o1 = atomicOr(&visited[s1 >> 5], 1u << (s1 & 31));
+            }
+            if (!heap.pop_warp(heap_size, lane)) {
+                if (lane == 0) heap.pop(heap_size);
+            }
             heap_size -= 1;
             cycles += 1;
             __syncwarp();
+            /* Speculation: unless this hop finds something closer, the new root is expanded next.
+             * Its neighbour row is requested now and only consumed one hop later. */
+            if (heap_size) {
+                pre_node = heap.root().s;
+                uint32_t const* next_row = ix.nbr0 + (size_t)pre_node * ix.m0_stride;
+                pre_s0 = lane < (int)ix.m0 ? __ldg(next_row + lane) : EMPTY_SLOT;
+                pre_s1 = lane + 32 < (int)ix.m0 ? __ldg(next_row + lane + 32) : EMPTY_SLOT;
+            } else
+                pre_node = EMPTY_SLOT;
+            PHASE(pc1)
 
-            /* visits.reserve(): keep the table at most half full so probing terminates quickly */
-            if ((visited_count + ix.m0) * 2 > a.visited_cap) { status = STATUS_VISITED_OVERFLOW; break; }
-
-            /* test-and-set every neighbour at once, compact the unseen ones in stored order */
-            uint32_t const* row = ix.nbr0 + (size_t)cur.s * ix.m0_stride;
+            /* compact the unseen neighbours in stored order */
             uint32_t ncand = 0;
-            for (uint32_t b = 0; b < ix.m0; b += 32) {
-                uint32_t i = b + lane;
-                uint32_t s = i < ix.m0 ? __ldg(row + i) : EMPTY_SLOT;
-                bool fresh = false;
-                if (s != EMPTY_SLOT) {
-                    uint32_t h = hash_slot(s) & vmask;
-                    for (;;) {
-                        uint32_t old = atomicCAS(&visited[h], EMPTY_SLOT, s);
-                        if (old == EMPTY_SLOT) { fresh = true; break; }
-                        if (old == s) break;
-                        h = (h + 1) & vmask;
-                    }
+            if (bitmap) {
+                bool f0 = s0 != EMPTY_SLOT && !((o0 >> (s0 & 31)) & 1u);
+                bool f1 = s1 != EMPTY_SLOT && !((o1 >> (s1 & 31)) & 1u);
+                uint32_t bal0 = __ballot_sync(0xffffffffu, f0), bal1 = __ballot_sync(0xffffffffu, f1);
+                uint32_t const lt = (1u << lane) - 1;
+                if (f0) cand_s[__popc(bal0 & lt)] = s0;
+                ncand = __popc(bal0);
+                if (f1) cand_s[ncand + __popc(bal1 & lt)] = s1;
+                ncand += __popc(bal1);
+                for (uint32_t b = 64; b < ix.m0; b += 32) {
+                    uint32_t i = b + lane;
+                    uint32_t s = i < ix.m0 ? __ldg(row + i) : EMPTY_SLOT;
+                    uint32_t o = s != EMPTY_SLOT ? atomicOr(&visited[s >> 5], 1u << (s & 31)) : 0xFFFFFFFFu;
+                    bool f = s != EMPTY_SLOT && !((o >> (s & 31)) & 1u);
+                    uint32_t bal = __ballot_sync(0xffffffffu, f);
+                    if (f) cand_s[ncand + __popc(bal & lt)] = s;
+                    ncand += __popc(bal);
                 }
-                /* a slot listed twice in the same 32-chunk: the first occurrence is the fresh one */
-                uint32_t same = __match_any_sync(0xffffffffu, s);
-                bool any_fresh = (__ballot_sync(0xffffffffu, fresh) & same) != 0;
-                fresh = any_fresh && s != EMPTY_SLOT && (__ffs(same) - 1) == lane;
-                uint32_t bal = __ballot_sync(0xffffffffu, fresh);
-                if (fresh) cand_s[ncand + __popc(bal & ((1u << lane) - 1))] = s;
-                ncand += __popc(bal);
+            } else {
+                /* visits.reserve(): keep the table at most half full so probing terminates quickly */
+                if ((visited_count + ix.m0) * 2 > a.visited_cap) { status = STATUS_VISITED_OVERFLOW; break; }
+                for (uint32_t b = 0; b < ix.m0; b += 32) {
+                    uint32_t i = b + lane;
+                    uint32_t s = b == 0 ? s0 : (b == 32 ? s1 : (i < ix.m0 ? __ldg(row + i) : EMPTY_SLOT));
+                    bool fresh = false;
+                    if (s != EMPTY_SLOT) {
+                        uint32_t h = hash_slot(s) & vmask;
+                        for (;;) {
+                            uint32_t old = atomicCAS(&visited[h], EMPTY_SLOT, s);
+                            if (old == EMPTY_SLOT) { fresh = true; break; }
+                            if (old == s) break;
+                            h = (h + 1) & vmask;
+                        }
+                    }
+                    uint32_t bal = __ballot_sync(0xffffffffu, fresh);
+                    if (fresh) cand_s[ncand + __popc(bal & ((1u << lane) - 1))] = s;
+                    ncand += __popc(bal);
+                }
             }
             visited_count += ncand;
             __syncwarp();
+            PHASE(pc2)
             if (ncand == 0) continue;
 
-            measure_list<M>(ix, q4, qc, cand_s, cand_d, ncand, lane);
+            measure_list<M, STAGED>(ix, a, w, qc, ncand, lane);
             computed += ncand;
+            PHASE(pc4)
 
-            /* the reference's sequential accept loop, replayed in stored order */
-            for (uint32_t c = 0; c < ncand; ++c) {
-                float d = cand_d[c];
-                if (top_size < ef || d < radius) {
-                    uint32_t s = cand_s[c];
-                    if (heap_size >= a.heap_smem_cap + a.heap_spill_cap) { status = STATUS_HEAP_OVERFLOW; break; }
-                    if (lane == 0) heap.push(heap_size, cand_t{d, s});
-                    heap_size += 1;
-                    bool allowed = !ix.deleted_bits || !((ix.deleted_bits[s >> 5] >> (s & 31)) & 1u);
-                    if (allowed) {
-                        top_insert(top_d, top_s, top_size, ef, d, s, lane);
-                        radius = top_d[top_size - 1];
+            /* The reference's sequential accept loop, replayed in stored order. `radius` only shrinks
+             * and `top` only grows inside a hop, so a candidate that fails `|top|<ef || d<radius` at the
+             * start of the hop fails it at its turn as well: only the others are visited. */
+            for (uint32_t b = 0; b < ncand && status == STATUS_OK; b += 32) {
+                uint32_t c = b + lane;
+                bool maybe = c < ncand && (top_size < ef || cand_d[c] < radius);
+                uint32_t todo = __ballot_sync(0xffffffffu, maybe);
+                while (todo) {
+                    uint32_t c2 = b + (__ffs(todo) - 1);
+                    todo &= todo - 1;
+                    float d = cand_d[c2];
+                    if (top_size < ef || d < radius) {
+                        uint32_t s = cand_s[c2];
+                        if (heap_size + 2 >= a.heap_smem_cap + a.heap_spill_cap) { status = STATUS_HEAP_OVERFLOW; break; }
+                        heap.push(heap_size, cand_t{d, s}, lane);
+                        heap_size += 1;
+                        if (prof) { n_push += 1; max_heap = max(max_heap, heap_size); }
+                        bool allowed = !ix.deleted_bits || !((ix.deleted_bits[s >> 5] >> (s & 31)) & 1u);
+                        if (allowed) {
+                            if (topreg) {
+                                top_insert_reg(rtd, rts, top_size, ef, d, s, lane);
+                                radius = top_back_reg(rtd, top_size);
+                            } else {
+                                top_insert(top_d, top_s, top_size, ef, d, s, lane);
+                                radius = top_d[top_size - 1];
+                            }
+                        }
+                        __syncwarp();
                     }
-                    __syncwarp();
                 }
             }
+            PHASE(pc5)
             if (status != STATUS_OK) break;
         }
     }
@@ -325,15 +689,32 @@ __device__ void search_one(device_index_t const& ix, search_args_t const& a, uin
     /* ---- dump_to (index.hpp:2707-2722) ---- */
     __syncwarp();
     uint32_t count = top_size < k ? top_size : k;
-    for (uint32_t i = lane; i < k; i += 32) {
-        uint64_t key = 0;
-        uint32_t bits = SNAN_BITS;
-        if (i < count) {
-            key = ix.keys[top_s[i]];
-            bits = __float_as_uint(top_d[i]);
+    if (topreg) {
+#pragma unroll
+        for (int c = 0; c < TOP_E; ++c) {
+            uint32_t const i = (uint32_t)(c * 32 + lane);
+            if (c * 32 < (int)k && i < k) {
+                uint64_t key = 0;
+                uint32_t bits = SNAN_BITS;
+                if (i < count) {
+                    key = ix.keys[rts[c]];
+                    bits = __float_as_uint(rtd[c]);
+                }
+                a.out_keys[(size_t)qi * k + i] = key;
+                reinterpret_cast<uint32_t*>(a.out_dists)[(size_t)qi * k + i] = bits;
+            }
         }
-        a.out_keys[(size_t)qi * k + i] = key;
-        reinterpret_cast<uint32_t*>(a.out_dists)[(size_t)qi * k + i] = bits;
+    } else {
+        for (uint32_t i = lane; i < k; i += 32) {
+            uint64_t key = 0;
+            uint32_t bits = SNAN_BITS;
+            if (i < count) {
+                key = ix.keys[top_s[i]];
+                bits = __float_as_uint(top_d[i]);
+            }
+            a.out_keys[(size_t)qi * k + i] = key;
+            reinterpret_cast<uint32_t*>(a.out_dists)[(size_t)qi * k + i] = bits;
+        }
     }
     if (lane == 0) {
         a.out_counts[qi] = count;
@@ -342,68 +723,126 @@ __device__ void search_one(device_index_t const& ix, search_args_t const& a, uin
         a.status[qi] = status;
     }
     __syncwarp();
+    if (prof && lane == 0) {
+        uint32_t pc6 = (uint32_t)(clock64() - tp);
+        atomicAdd(a.phase_cycles + 0, (unsigned long long)pc0);
+        atomicAdd(a.phase_cycles + 1, (unsigned long long)pc1);
+        atomicAdd(a.phase_cycles + 2, (unsigned long long)pc2);
+        atomicAdd(a.phase_cycles + 3, (unsigned long long)w.t_wait);
+        atomicAdd(a.phase_cycles + 4, (unsigned long long)(pc4 - w.t_wait));
+        atomicAdd(a.phase_cycles + 5, (unsigned long long)pc5);
+        atomicAdd(a.phase_cycles + 6, (unsigned long long)pc6);
+        atomicAdd(a.phase_cycles + 7, 1ull);
+        atomicAdd(a.phase_cycles + 8, (unsigned long long)n_push);
+        atomicAdd(a.phase_cycles + 9, (unsigned long long)max_heap);
+        atomicMax(a.phase_cycles + 10, (unsigned long long)max_heap);
+    }
+#undef PHASE
 }
 
-template <class M>
-__global__ void __launch_bounds__(THREADS, 4) hnsw_search_kernel(device_index_t ix, search_args_t a) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t* my_smem = smem + (size_t)warp * a.smem_per_warp;
-    uint32_t const gw = blockIdx.x * WARPS_PER_BLOCK + warp;
-    uint32_t* visited = a.visited + (size_t)gw * a.visited_cap;
-    cand_t* spill = a.heap_spill + (size_t)gw * a.heap_spill_cap;
+template <class M, bool STAGED>
+__global__ void __launch_bounds__(THREADS, STAGED ? 8 : 16) hnsw_search_kernel(__grid_constant__ device_index_t const ix,
+                                                              __grid_constant__ search_args_t const a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    int const lane = threadIdx.x;
+    warp_ctx_t w;
+    w.q4 = reinterpret_cast<uint4*>(smem);
+    w.top_d = reinterpret_cast<float*>(smem + a.off_top_d);
+    w.top_s = reinterpret_cast<uint32_t*>(smem + a.off_top_s);
+    w.cand_s = reinterpret_cast<uint32_t*>(smem + a.off_cand_s);
+    w.cand_d = reinterpret_cast<float*>(smem + a.off_cand_d);
+    w.stage = smem + a.off_stage;
+    w.stage_addr = smem_u32(w.stage);
+    w.bars_addr = smem_u32(smem + a.off_bars);
+    w.phase = 0;
+    heap_t heap{smem_u32(smem + a.off_heap), a.heap_spill + (size_t)blockIdx.x * a.heap_spill_cap, a.heap_smem_cap};
+    uint32_t* visited = a.visited + (size_t)blockIdx.x * (a.visited_bitmap_words ? a.visited_bitmap_words : a.visited_cap);
+    if constexpr (STAGED) {
+        if (lane < 16) mbar_init(w.bars_addr + 8u * lane, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+    }
     for (;;) {
         uint32_t item = 0;
         if (lane == 0) item = atomicAdd(a.work_counter, 1u);
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= a.nq) break;
         uint32_t qi = a.query_list ? a.query_list[item] : item;
-        search_one<M>(ix, a, qi, my_smem, visited, spill, lane);
+        search_one<M, STAGED>(ix, a, qi, w, heap, visited, lane);
     }
+}
+
+/* ---- freeze-time helper: squared norms in the metric's summation order -------------------------- */
+
+__global__ void norms_f32_kernel(device_index_t ix, float* norms) {
+    uint32_t const lane = threadIdx.x & 31, group = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    uint32_t const slot = group < ix.n ? group : ix.n - 1; /* whole warps stay converged for the shuffles */
+    uint4 const* v = reinterpret_cast<uint4 const*>(ix.vectors + (size_t)slot * ix.vec_stride);
+    float b2 = cos_f32_t::self_dot(v, ix.chunks16, (int)lane);
+    if (group < ix.n && (lane & 3) == 0) norms[group] = b2;
+}
+
+bool search_needs_norms(uint32_t metric, uint32_t scalar) { return metric == METRIC_COS && scalar == SCALAR_F32; }
+
+cudaError_t search_compute_norms(device_index_t const& ix, float* norms, cudaStream_t stream) {
+    if (!ix.n) return cudaSuccess;
+    uint32_t const threads = 256, groups_per_block = threads / 4;
+    norms_f32_kernel<<<(ix.n + groups_per_block - 1) / groups_per_block, threads, 0, stream>>>(ix, norms);
+    return cudaGetLastError();
 }
 
 /* ---- host-side dispatch --------------------------------------------------------------------- */
 
-template <class M>
+template <class M, bool STAGED>
 static cudaError_t launch_t(device_index_t const& ix, search_args_t const& a, int blocks, size_t smem, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(hnsw_search_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(hnsw_search_kernel<M, STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    hnsw_search_kernel<M><<<blocks, THREADS, smem, stream>>>(ix, a);
+    hnsw_search_kernel<M, STAGED><<<blocks, THREADS, smem, stream>>>(ix, a);
     return cudaGetLastError();
 }
 
-template <class M> static cudaError_t occupancy_t(int* blocks_per_sm, size_t smem) {
-    cudaError_t e = cudaFuncSetAttribute(hnsw_search_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <class M, bool STAGED> static cudaError_t occupancy_t(int* blocks_per_sm, size_t smem) {
+    cudaError_t e = cudaFuncSetAttribute(hnsw_search_kernel<M, STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, hnsw_search_kernel<M>, THREADS, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, hnsw_search_kernel<M, STAGED>, THREADS, smem);
 }
 
+#define DISPATCH_M(FN, M, ...) return staged ? FN<M, true>(__VA_ARGS__) : FN<M, false>(__VA_ARGS__)
 #define DISPATCH(FN, ...)                                                                                  \
     switch (ix.scalar) {                                                                                   \
     case SCALAR_F32:                                                                                       \
-        if (ix.metric == METRIC_L2SQ) return FN<l2sq_f32_t>(__VA_ARGS__);                                  \
-        if (ix.metric == METRIC_IP) return FN<ip_f32_t>(__VA_ARGS__);                                      \
-        if (ix.metric == METRIC_COS) return FN<cos_f32_t>(__VA_ARGS__);                                    \
+        if (ix.metric == METRIC_L2SQ) DISPATCH_M(FN, l2sq_f32_t, __VA_ARGS__);                             \
+        if (ix.metric == METRIC_IP) DISPATCH_M(FN, ip_f32_t, __VA_ARGS__);                                 \
+        if (ix.metric == METRIC_COS) DISPATCH_M(FN, cos_f32_t, __VA_ARGS__);                               \
         break;                                                                                             \
     case SCALAR_I8:                                                                                        \
-        if (ix.metric == METRIC_L2SQ) return FN<l2sq_i8_t<4>>(__VA_ARGS__);                                \
-        if (ix.metric == METRIC_IP) return FN<ip_i8_t<4>>(__VA_ARGS__);                                    \
-        if (ix.metric == METRIC_COS) return FN<cos_i8_t<4>>(__VA_ARGS__);                                  \
+        if (ix.metric == METRIC_L2SQ) DISPATCH_M(FN, l2sq_i8_t<4>, __VA_ARGS__);                           \
+        if (ix.metric == METRIC_IP) DISPATCH_M(FN, ip_i8_t<4>, __VA_ARGS__);                               \
+        if (ix.metric == METRIC_COS) DISPATCH_M(FN, cos_i8_t<4>, __VA_ARGS__);                             \
         break;                                                                                             \
     case SCALAR_B1:                                                                                        \
-        if (ix.metric == METRIC_HAMMING) return FN<hamming_b1_t<2>>(__VA_ARGS__);                          \
-        if (ix.metric == METRIC_TANIMOTO || ix.metric == METRIC_JACCARD) return FN<tanimoto_b1_t<2>>(__VA_ARGS__); \
-        if (ix.metric == METRIC_SORENSEN) return FN<sorensen_b1_t<2>>(__VA_ARGS__);                        \
+        if (ix.metric == METRIC_HAMMING) return FN<hamming_b1_t<2>, false>(__VA_ARGS__);                   \
+        if (ix.metric == METRIC_TANIMOTO || ix.metric == METRIC_JACCARD) return FN<tanimoto_b1_t<2>, false>(__VA_ARGS__); \
+        if (ix.metric == METRIC_SORENSEN) return FN<sorensen_b1_t<2>, false>(__VA_ARGS__);                 \
         break;                                                                                             \
     default: break;                                                                                        \
     }                                                                                                      \
     return cudaErrorInvalidValue;
 
+/* vectors of at least this many bytes are fetched with TMA bulk copies into shared memory */
+constexpr uint32_t STAGED_MIN_BYTES = 256;
+
+bool search_is_staged(device_index_t const& ix) { return ix.scalar != SCALAR_B1 && ix.vec_stride >= STAGED_MIN_BYTES; }
+int search_stage_slots(device_index_t const& ix) { return search_is_staged(ix) ? 8 : 0; /* 32 / LPV */ }
+
 cudaError_t search_launch(device_index_t const& ix, search_args_t const& a, int blocks, size_t smem, cudaStream_t stream) {
+    bool const staged = search_is_staged(ix);
     DISPATCH(launch_t, ix, a, blocks, smem, stream)
 }
 
 cudaError_t search_occupancy(device_index_t const& ix, int* blocks_per_sm, size_t smem) {
+    bool const staged = search_is_staged(ix);
     DISPATCH(occupancy_t, blocks_per_sm, smem)
 }
 
@@ -417,6 +856,6 @@ bool search_supported(uint32_t metric, uint32_t scalar) {
     }
 }
 
-int search_warps_per_block() { return WARPS_PER_BLOCK; }
+int search_warps_per_block() { return 1; }
 
 } // namespace usearch_b200

@@ -48,7 +48,7 @@ EXPORTED_SYMBOLS = [
     "usearch_exact_search", "usearch_clear",
     # additive
     "usearch_search_many", "usearch_b200_search_many_device", "usearch_b200_search_many_stats",
-    "usearch_b200_device", "usearch_b200_kernel_launches", "usearch_b200_last_kernel_ms",
+    "usearch_b200_profile_phases", "usearch_b200_device", "usearch_b200_kernel_launches", "usearch_b200_last_kernel_ms",
     "usearch_b200_bytes_per_vector", "usearch_b200_max_level",
 ]
 
@@ -95,6 +95,7 @@ def load_library() -> C.CDLL:
     lib.usearch_b200_search_many_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t,
                                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                     C.c_void_p, err]
+    lib.usearch_b200_profile_phases.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.usearch_b200_device.argtypes = [C.c_void_p]
     lib.usearch_b200_kernel_launches.restype = C.c_uint64
     lib.usearch_b200_kernel_launches.argtypes = [C.c_void_p]
@@ -324,6 +325,15 @@ class Index:
             n = int(counts[0])
             return Matches(keys[0, :n], distances[0, :n], vm, cd)
         return BatchMatches(keys, distances, counts, vm, cd)
+
+    def profile_phases(self, enable: bool = True) -> dict:
+        """Read (then reset) the kernel's per-phase cycle counters; see include/usearch_b200.h."""
+        out = np.zeros(16, dtype=np.uint64)
+        self._lib.usearch_b200_profile_phases(self._h, int(enable), out.ctypes.data_as(C.c_void_p))
+        names = ["setup_descent", "heap_pop", "row_visited", "vector_wait", "distance_math", "accept", "output"]
+        q = max(int(out[7]), 1)
+        return {"queries": int(out[7]), **{n: float(out[i]) / q for i, n in enumerate(names)},
+                "pushes": float(out[8]) / q, "avg_max_heap": float(out[9]) / q, "max_heap": int(out[10])}
 
     def search_device(self, queries_ptr: int, nq: int, stride: int, count: int, keys_ptr: int, distances_ptr: int,
                       counts_ptr: int, computed_ptr: int = 0, visited_ptr: int = 0, stream: int = 0) -> None:
