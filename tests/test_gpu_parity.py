@@ -23,6 +23,10 @@ CASES = [
     ("l2sq", "f32", 5000, 32, 16, 300, 40, 64),     # ef > 256: shared-memory `top`, k > 32, DIRECT kernel
     ("ip", "f32", 6000, 128, 16, 300, 50, 64),      # ef > 256 on the STAGED (TMA) kernel
     ("cos", "f32", 4000, 64, 40, 256, 100, 64),     # M0 = 80 > 64 neighbours per row, ef == 256
+    ("cos", "f16", 6000, 768, 32, 128, 10, 128),    # one lane per vector, 32 TMA slots per pass
+    ("l2sq", "f16", 4000, 100, 16, 64, 10, 128),    # 200-byte vectors: DIRECT kernel, ragged tail
+    ("ip", "bf16", 4000, 256, 16, 64, 10, 128),
+    ("cos", "bf16", 3000, 96, 16, 64, 10, 128),
 ]
 
 

@@ -384,11 +384,12 @@ char const* frozen_index_t::plan(uint32_t k, uint32_t visited_cap_override, laun
     pl.off_top_s = off; off += top_smem;
     pl.off_cand_s = off; off += list_cap * 4;
     pl.off_cand_d = off; off += list_cap * 4;
-    pl.off_bars = off; off += 128; /* up to 16 mbarriers */
+    pl.off_bars = off; off += 256; /* 32 mbarriers */
     off = round_up(off, 128);
     pl.off_stage = off;
     int const slots = search_stage_slots(d); /* slots of one set: 32 / LPV */
-    pl.stage_stride = slots ? round_up((uint32_t)d.vec_stride, 128) + 64 : 0;
+    /* slot stride = 16*LPV mod 128 bytes: the lanes of a quarter-warp then read disjoint banks */
+    pl.stage_stride = slots ? round_up((uint32_t)d.vec_stride, 128) + 16u * (uint32_t)search_lanes_per_vector(d) : 0;
     /* an SM has 228 KB of shared memory and charges 1 KB per resident CTA on top of its request */
     size_t const smem_sm = 228 * 1024, cta_tax = 1024, smem_cta_max = 227 * 1024;
     uint32_t const min_heap = 128 * 8;
@@ -398,6 +399,7 @@ char const* frozen_index_t::plan(uint32_t k, uint32_t visited_cap_override, laun
     if (slots) {
         size_t const two = off + 2 * (size_t)slots * pl.stage_stride + min_heap + cta_tax;
         pl.stage_sets = (forced_sets == 1 || forced_sets == 2) ? (uint32_t)forced_sets : (smem_sm / two >= 4 ? 2u : 1u);
+        if (slots > 16) pl.stage_sets = 1; /* one parity bit per slot in a 32-bit word */
     }
     off += (uint32_t)slots * pl.stage_sets * pl.stage_stride;
     pl.off_heap = off;

@@ -24,6 +24,7 @@ bool search_supported(uint32_t metric, uint32_t scalar);
 int search_warps_per_block();
 bool search_is_staged(device_index_t const& ix);
 int search_stage_slots(device_index_t const& ix);
+int search_lanes_per_vector(device_index_t const& ix);
 bool search_needs_norms(uint32_t metric, uint32_t scalar);
 cudaError_t search_compute_norms(device_index_t const& ix, float* norms, cudaStream_t stream);
 

@@ -149,6 +149,126 @@ struct cos_f32_t {
     }
 };
 
+/* ---- f16 / bf16 --------------------------------------------------------------------------- */
+/*
+ *  simsimd_{l2sq,dot,cos}_{f16,bf16}_haswell (spatial.h:1098-1200): 8 f32 accumulators, element i ->
+ *  accumulator i mod 8, operands widened to f32, one fma per element; horizontal reduce through f64
+ *  (dot.h:857-869, :844-855): s_k = (double)v[k] + (double)v[k+4]; (s0 + s2) + (s1 + s3).
+ *  A 16-byte chunk holds one element of EVERY accumulator, so the chains cannot be split across lanes:
+ *  ONE lane walks a whole vector (LPV = 1, 32 candidate vectors per pass, no cross-lane reduction) and
+ *  the query chunk it needs is the same address for all 32 lanes — a shared-memory broadcast.
+ *  The native AVX512-FP16 kernel of a Sapphire Rapids host accumulates in fp16 and is not reproducible
+ *  (SURVEY.md finding 5); the oracle pins this f32-accumulating order instead.
+ */
+struct f16_conv_t {
+    static __device__ __forceinline__ void widen(uint32_t w, float& lo, float& hi) {
+        float2 f = __half22float2(*reinterpret_cast<__half2 const*>(&w));
+        lo = f.x;
+        hi = f.y;
+    }
+};
+struct bf16_conv_t {
+    static __device__ __forceinline__ void widen(uint32_t w, float& lo, float& hi) {
+        lo = __uint_as_float(w << 16);
+        hi = __uint_as_float(w & 0xFFFF0000u);
+    }
+};
+
+__device__ __forceinline__ double reduce8_f64(float const v[8]) {
+    double s0 = __dadd_rn((double)v[0], (double)v[4]), s1 = __dadd_rn((double)v[1], (double)v[5]);
+    double s2 = __dadd_rn((double)v[2], (double)v[6]), s3 = __dadd_rn((double)v[3], (double)v[7]);
+    return __dadd_rn(__dadd_rn(s0, s2), __dadd_rn(s1, s3));
+}
+
+template <class C> __device__ __forceinline__ void widen8(uint4 x, float (&f)[8]) {
+    C::widen(x.x, f[0], f[1]);
+    C::widen(x.y, f[2], f[3]);
+    C::widen(x.z, f[4], f[5]);
+    C::widen(x.w, f[6], f[7]);
+}
+
+template <class C> struct l2sq_half_t {
+    static constexpr int LPV = 1;
+    static constexpr bool NORMS = false;
+    template <class Q> static __device__ __forceinline__ float finalize(float raw, Q, float) { return raw; }
+    struct acc_t { float v[8]; };
+    struct qconst_t {};
+    static __device__ __forceinline__ void init(acc_t& a) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a.v[k] = 0.f;
+    }
+    static __device__ __forceinline__ void step(acc_t& a, uint4 b, uint4 q) {
+        float fb[8], fq[8];
+        widen8<C>(b, fb);
+        widen8<C>(q, fq);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float x = __fsub_rn(fq[k], fb[k]);
+            a.v[k] = __fmaf_rn(x, x, a.v[k]);
+        }
+    }
+    static __device__ __forceinline__ float finish(acc_t const& a, qconst_t) { return __double2float_rn(reduce8_f64(a.v)); }
+    static __device__ __forceinline__ qconst_t prepare(uint4 const*, uint32_t, int) { return {}; }
+};
+
+template <class C> struct ip_half_t {
+    static constexpr int LPV = 1;
+    static constexpr bool NORMS = false;
+    template <class Q> static __device__ __forceinline__ float finalize(float raw, Q, float) { return raw; }
+    struct acc_t { float v[8]; };
+    struct qconst_t {};
+    static __device__ __forceinline__ void init(acc_t& a) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a.v[k] = 0.f;
+    }
+    static __device__ __forceinline__ void step(acc_t& a, uint4 b, uint4 q) {
+        float fb[8], fq[8];
+        widen8<C>(b, fb);
+        widen8<C>(q, fq);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a.v[k] = __fmaf_rn(fq[k], fb[k], a.v[k]);
+    }
+    static __device__ __forceinline__ float finish(acc_t const& a, qconst_t) {
+        return __fsub_rn(1.0f, __double2float_rn(reduce8_f64(a.v)));
+    }
+    static __device__ __forceinline__ qconst_t prepare(uint4 const*, uint32_t, int) { return {}; }
+};
+
+/* cos: ||b||^2 comes from `norms` (same chain, computed at freeze); normalisation in f32 like
+ * _simsimd_cos_normalize_f32_haswell (spatial.h:1050-1080), IEEE instead of rsqrt_ps + Newton. */
+template <class C> struct cos_half_t {
+    static constexpr int LPV = 1;
+    static constexpr bool NORMS = true;
+    struct acc_t { float v[8]; };
+    struct qconst_t { float a2; };
+    static __device__ __forceinline__ void init(acc_t& a) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a.v[k] = 0.f;
+    }
+    static __device__ __forceinline__ void step(acc_t& a, uint4 b, uint4 q) {
+        float fb[8], fq[8];
+        widen8<C>(b, fb);
+        widen8<C>(q, fq);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a.v[k] = __fmaf_rn(fq[k], fb[k], a.v[k]);
+    }
+    static __device__ __forceinline__ float finish(acc_t const& a, qconst_t) { return __double2float_rn(reduce8_f64(a.v)); }
+    static __device__ __forceinline__ float finalize(float ab, qconst_t qc, float b2) { return cos_normalize_f32(ab, qc.a2, b2); }
+    static __device__ __forceinline__ float self_dot(uint4 const* v4, uint32_t chunks16, int) {
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (uint32_t j = 0; j < chunks16; ++j) {
+            float f[8];
+            widen8<C>(v4[j], f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = __fmaf_rn(f[k], f[k], v[k]);
+        }
+        return __double2float_rn(reduce8_f64(v));
+    }
+    static __device__ __forceinline__ qconst_t prepare(uint4 const* q4, uint32_t chunks16, int lane) {
+        return {self_dot(q4, chunks16, lane)};
+    }
+};
+
 /* ---- i8 --------------------------------------------------------------------------------- */
 
 template <int LPV_> struct ip_i8_t {

@@ -402,7 +402,7 @@ __device__ __forceinline__ void measure_staged(device_index_t const& ix, search_
         }
         float d = M::finish(acc, qc);
         if (act && sub == 0) w.cand_d[base + g] = d;
-        w.phase ^= ((1u << cnt) - 1u) << ((p % nsets) * VPP);
+        w.phase ^= (cnt >= 32u ? 0xFFFFFFFFu : (1u << cnt) - 1u) << ((p % nsets) * VPP);
         __syncwarp(); /* every lane is done with this set before it is refilled */
         if (p + nsets < npass) issue(p + nsets);
     }
@@ -758,7 +758,7 @@ __global__ void __launch_bounds__(THREADS, STAGED ? 8 : 16) hnsw_search_kernel(_
     heap_t heap{smem_u32(smem + a.off_heap), a.heap_spill + (size_t)blockIdx.x * a.heap_spill_cap, a.heap_smem_cap};
     uint32_t* visited = a.visited + (size_t)blockIdx.x * (a.visited_bitmap_words ? a.visited_bitmap_words : a.visited_cap);
     if constexpr (STAGED) {
-        if (lane < 16) mbar_init(w.bars_addr + 8u * lane, 1);
+        mbar_init(w.bars_addr + 8u * lane, 1); /* 32 mbarriers: 2 sets x 8 slots (LPV 4) or 1 set x 32 slots (LPV 1) */
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
@@ -775,20 +775,31 @@ __global__ void __launch_bounds__(THREADS, STAGED ? 8 : 16) hnsw_search_kernel(_
 
 /* ---- freeze-time helper: squared norms in the metric's summation order -------------------------- */
 
-__global__ void norms_f32_kernel(device_index_t ix, float* norms) {
-    uint32_t const lane = threadIdx.x & 31, group = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+template <class M> __global__ void norms_kernel(device_index_t ix, float* norms) {
+    constexpr int LPV = M::LPV;
+    uint32_t const lane = threadIdx.x & 31, group = (blockIdx.x * blockDim.x + threadIdx.x) / LPV;
     uint32_t const slot = group < ix.n ? group : ix.n - 1; /* whole warps stay converged for the shuffles */
     uint4 const* v = reinterpret_cast<uint4 const*>(ix.vectors + (size_t)slot * ix.vec_stride);
-    float b2 = cos_f32_t::self_dot(v, ix.chunks16, (int)lane);
-    if (group < ix.n && (lane & 3) == 0) norms[group] = b2;
+    float b2 = M::self_dot(v, ix.chunks16, (int)lane);
+    if (group < ix.n && (lane % LPV) == 0) norms[group] = b2;
 }
 
-bool search_needs_norms(uint32_t metric, uint32_t scalar) { return metric == METRIC_COS && scalar == SCALAR_F32; }
+bool search_needs_norms(uint32_t metric, uint32_t scalar) {
+    return metric == METRIC_COS && (scalar == SCALAR_F32 || scalar == SCALAR_F16 || scalar == SCALAR_BF16);
+}
 
 cudaError_t search_compute_norms(device_index_t const& ix, float* norms, cudaStream_t stream) {
     if (!ix.n) return cudaSuccess;
-    uint32_t const threads = 256, groups_per_block = threads / 4;
-    norms_f32_kernel<<<(ix.n + groups_per_block - 1) / groups_per_block, threads, 0, stream>>>(ix, norms);
+    uint32_t const threads = 256;
+    if (ix.scalar == SCALAR_F32) {
+        uint32_t const per_block = threads / 4;
+        norms_kernel<cos_f32_t><<<(ix.n + per_block - 1) / per_block, threads, 0, stream>>>(ix, norms);
+    } else if (ix.scalar == SCALAR_F16) {
+        norms_kernel<cos_half_t<f16_conv_t>><<<(ix.n + threads - 1) / threads, threads, 0, stream>>>(ix, norms);
+    } else if (ix.scalar == SCALAR_BF16) {
+        norms_kernel<cos_half_t<bf16_conv_t>><<<(ix.n + threads - 1) / threads, threads, 0, stream>>>(ix, norms);
+    } else
+        return cudaErrorInvalidValue;
     return cudaGetLastError();
 }
 
@@ -816,6 +827,16 @@ template <class M, bool STAGED> static cudaError_t occupancy_t(int* blocks_per_s
         if (ix.metric == METRIC_IP) DISPATCH_M(FN, ip_f32_t, __VA_ARGS__);                                 \
         if (ix.metric == METRIC_COS) DISPATCH_M(FN, cos_f32_t, __VA_ARGS__);                               \
         break;                                                                                             \
+    case SCALAR_F16:                                                                                       \
+        if (ix.metric == METRIC_L2SQ) DISPATCH_M(FN, l2sq_half_t<f16_conv_t>, __VA_ARGS__);                \
+        if (ix.metric == METRIC_IP) DISPATCH_M(FN, ip_half_t<f16_conv_t>, __VA_ARGS__);                    \
+        if (ix.metric == METRIC_COS) DISPATCH_M(FN, cos_half_t<f16_conv_t>, __VA_ARGS__);                  \
+        break;                                                                                             \
+    case SCALAR_BF16:                                                                                      \
+        if (ix.metric == METRIC_L2SQ) DISPATCH_M(FN, l2sq_half_t<bf16_conv_t>, __VA_ARGS__);               \
+        if (ix.metric == METRIC_IP) DISPATCH_M(FN, ip_half_t<bf16_conv_t>, __VA_ARGS__);                   \
+        if (ix.metric == METRIC_COS) DISPATCH_M(FN, cos_half_t<bf16_conv_t>, __VA_ARGS__);                 \
+        break;                                                                                             \
     case SCALAR_I8:                                                                                        \
         if (ix.metric == METRIC_L2SQ) DISPATCH_M(FN, l2sq_i8_t<4>, __VA_ARGS__);                           \
         if (ix.metric == METRIC_IP) DISPATCH_M(FN, ip_i8_t<4>, __VA_ARGS__);                               \
@@ -834,7 +855,8 @@ template <class M, bool STAGED> static cudaError_t occupancy_t(int* blocks_per_s
 constexpr uint32_t STAGED_MIN_BYTES = 256;
 
 bool search_is_staged(device_index_t const& ix) { return ix.scalar != SCALAR_B1 && ix.vec_stride >= STAGED_MIN_BYTES; }
-int search_stage_slots(device_index_t const& ix) { return search_is_staged(ix) ? 8 : 0; /* 32 / LPV */ }
+int search_lanes_per_vector(device_index_t const& ix) { return (ix.scalar == SCALAR_F16 || ix.scalar == SCALAR_BF16) ? 1 : 4; }
+int search_stage_slots(device_index_t const& ix) { return search_is_staged(ix) ? 32 / search_lanes_per_vector(ix) : 0; }
 
 cudaError_t search_launch(device_index_t const& ix, search_args_t const& a, int blocks, size_t smem, cudaStream_t stream) {
     bool const staged = search_is_staged(ix);
@@ -849,6 +871,8 @@ cudaError_t search_occupancy(device_index_t const& ix, int* blocks_per_sm, size_
 bool search_supported(uint32_t metric, uint32_t scalar) {
     switch (scalar) {
     case SCALAR_F32:
+    case SCALAR_F16:
+    case SCALAR_BF16:
     case SCALAR_I8: return metric == METRIC_L2SQ || metric == METRIC_IP || metric == METRIC_COS;
     case SCALAR_B1:
         return metric == METRIC_HAMMING || metric == METRIC_TANIMOTO || metric == METRIC_JACCARD || metric == METRIC_SORENSEN;
