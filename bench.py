@@ -299,18 +299,13 @@ def run_b200_arm(a):
     vis_dev = torch.zeros(B, dtype=torch.int32, device=device)
     stream = torch.cuda.current_stream(device)
 
-    gathered_k = [torch.zeros_like(keys_dev) for _ in range(world)] if world > 1 else None
-    gathered_d = [torch.zeros_like(dist_dev) for _ in range(world)] if world > 1 else None
+    from usearch_b200 import sharded
 
     def merge_topk():
-        """The single exchange step of the sharded path: all-gather per-shard top-k over NCCL, then a
-        k-way merge ordered by (distance, shard, rank-in-shard) — python/lib.cpp:350-391 `merge_into`."""
-        dist.all_gather(gathered_k, keys_dev)
-        dist.all_gather(gathered_d, dist_dev)
-        cat_d = torch.cat(gathered_d, 1)
-        cat_d = torch.where(torch.isnan(cat_d), torch.full_like(cat_d, float("inf")), cat_d)
-        order = torch.sort(cat_d, dim=1, stable=True).indices[:, :k]
-        return torch.gather(torch.cat(gathered_k, 1), 1, order), torch.gather(cat_d, 1, order)
+        """The single exchange step of the sharded path (usearch_b200/sharded.py): one NCCL all-gather of the
+        per-shard top-k, then a stable k-way merge ordered by (distance, shard, rank-in-shard)."""
+        mk, md, _ = sharded.merge_topk(keys_dev, dist_dev, cnt_dev, k)
+        return mk, md
 
     def step_device(s: int):
         qs = q_dev[s * B:(s + 1) * B]
@@ -376,6 +371,7 @@ def run_b200_arm(a):
         if world > 1:
             keys_dev.copy_(torch.from_numpy(res.keys.view(np.int64)), non_blocking=False)
             dist_dev.copy_(torch.from_numpy(res.distances), non_blocking=False)
+            cnt_dev.copy_(torch.from_numpy(res.counts.astype(np.int32)), non_blocking=False)
             mk, md = merge_topk()
             mk.cpu()
     barrier()
