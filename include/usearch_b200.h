@@ -173,6 +173,16 @@ size_t usearch_b200_search_many_stats(usearch_index_t index, void const* queries
 
 /* Introspection for tests / bench: CUDA device ordinal, kernel launches issued so far by this
  * handle, duration in milliseconds of the most recent search kernel (CUDA events on its stream). */
+/* Device-side counterpart of usearch_filtered_search (usearch.h:391-395) for the one predicate family that
+ * can run on a GPU: "the key is in this set". `allowed_keys` (host memory, any order, may be empty) is turned
+ * into a bitmap over slots; the predicate is applied where the reference applies its callback
+ * (index_dense.hpp:2078-2083, index.hpp:4201/4236): rejected members are still traversed, never returned. */
+size_t usearch_b200_filtered_search_many(usearch_index_t index, void const* queries, size_t queries_count,
+                                         size_t queries_stride, usearch_scalar_kind_t query_kind, size_t count,
+                                         usearch_key_t const* allowed_keys, size_t allowed_count, usearch_key_t* keys,
+                                         usearch_distance_t* distances, size_t* counts, uint64_t* computed_distances,
+                                         uint64_t* visited_members, usearch_error_t* error);
+
 /* Phase introspection of the search kernel: enable != 0 turns on (and zeroes) sixteen device-side
  * counters summed over all queries since; `counters16` (may be NULL) first receives the current values:
  * cycles of setup+descent | heap pop | row + visited test | vector wait | distance math | accept replay |

@@ -78,6 +78,8 @@ def ref_lib(flavour: str = "parity") -> C.CDLL | None:
     lib.ref_load_path.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_char_p)]
     lib.ref_search_many.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int,
                                     _u64p, _f32p, _u64p, _u64p, _u64p, C.POINTER(C.c_char_p)]
+    lib.ref_filtered_search_many_f32.argtypes = [C.c_void_p, _f32p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, _u64p,
+                                                 C.c_size_t, _u64p, _f32p, _u64p, _u64p, _u64p, C.POINTER(C.c_char_p)]
     lib.ref_cast_from_f32.restype = C.c_size_t
     lib.ref_cast_from_f32.argtypes = [C.c_int, _f32p, C.c_size_t, C.c_void_p]
     lib.ref_hardware_threads.restype = C.c_size_t
@@ -183,6 +185,23 @@ class RefIndex:
         _check(err)
         return keys, dist, counts, computed, visited
 
+
+def _ref_filtered_search(self, queries: np.ndarray, k: int, allowed_keys: np.ndarray, threads: int = 1):
+    queries = np.ascontiguousarray(queries, dtype=np.float32)
+    allowed = np.sort(np.ascontiguousarray(allowed_keys, dtype=np.uint64))
+    nq = queries.shape[0]
+    keys = np.zeros((nq, k), dtype=np.uint64)
+    dist = np.zeros((nq, k), dtype=np.float32)
+    counts, computed, visited = (np.zeros(nq, dtype=np.uint64) for _ in range(3))
+    err = C.c_char_p()
+    self.lib.ref_filtered_search_many_f32(self.h, _ptr(queries, _f32p), nq, queries.strides[0], k, threads,
+                                          _ptr(allowed, _u64p), allowed.size, _ptr(keys, _u64p), _ptr(dist, _f32p),
+                                          _ptr(counts, _u64p), _ptr(computed, _u64p), _ptr(visited, _u64p), C.byref(err))
+    _check(err)
+    return keys, dist, counts, computed, visited
+
+
+RefIndex.filtered_search = _ref_filtered_search
 
 _port_lib: C.CDLL | None = None
 

@@ -19,6 +19,7 @@
  *  Everything that decides *which labels come back* — descent, best-first expansion, containers,
  *  tie-breaking — is the reference's own code. Only the distance function is swappable.
  */
+#include <algorithm>
 #include <atomic>
 #include <cstdint>
 #include <cstring>
@@ -327,6 +328,28 @@ void ref_search_many(void* h, void const* queries, std::size_t nq, std::size_t s
         (void)ok;
     });
     *error = first_error.load();
+}
+
+/* `filtered_search` (index_dense.hpp:774-779) with the predicate "key is in the sorted array `allowed`";
+ * f32-only convenience for the parity tests of the device-side filter. */
+void ref_filtered_search_many_f32(void* h, float const* queries, std::size_t nq, std::size_t stride_bytes,
+                                  std::size_t wanted, std::size_t threads, std::uint64_t const* allowed,
+                                  std::size_t allowed_count, std::uint64_t* keys, float* distances, std::uint64_t* counts,
+                                  std::uint64_t* computed, std::uint64_t* visited, char const** error) {
+    *error = nullptr;
+    auto* r = static_cast<ref_index_t*>(h);
+    if (!ensure_threads(r, r->index.size(), threads)) {
+        *error = "Out of memory!";
+        return;
+    }
+    auto const* base = reinterpret_cast<byte_t const*>(queries);
+    auto predicate = [=](std::uint64_t key) noexcept { return std::binary_search(allowed, allowed + allowed_count, key); };
+    parallel_for(nq, threads, [&](std::size_t thread, std::size_t i) {
+        auto result = r->index.filtered_search(reinterpret_cast<f32_t const*>(base + i * stride_bytes), wanted, predicate, thread);
+        counts[i] = result.dump_to(keys + i * wanted, distances + i * wanted, wanted);
+        if (computed) computed[i] = result.computed_distances;
+        if (visited) visited[i] = result.visited_members;
+    });
 }
 
 /* The reference's query-side casts (index_plugins.hpp:1105-1224), exposed so tests can check the

@@ -82,3 +82,51 @@ def test_visited_modes_and_scratch_retry(mode):
     launches = int(out.stdout.split("launches")[1].split()[0])
     if mode == "hash":  # bitmap `visits` cannot overflow; its heap head alone (shared memory) holds these searches
         assert launches >= 2, "expected at least one retry launch with 64x undersized scratch: " + out.stdout
+
+
+@pytest.mark.skipif(not common.have_reference(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("fraction", [0.5, 0.05, 0.0])
+def test_filtered_search_matches_reference(fraction):
+    """Device-side `key in set` predicate vs the reference's filtered_search with the same predicate
+    (cpp/test.cpp:1105-1145): rejected members are traversed but never returned; some keys are also removed."""
+    from usearch_b200.index import Index
+    n, d, m, ef, k = 8000, 96, 16, 64, 10
+    base, q = common.make_collection(n, d, "f32", 200)
+    ref, _ = common.build_reference_blob(base, "cos", "f32", d, m, threads=16, keys=np.arange(n, dtype=np.uint64) * 7 + 3)
+    for key in range(3, 3 + 7 * 400, 7 * 4):
+        ref.remove(key)
+    blob = ref.save()
+    ref.pin_metric(True)
+    ref.change_expansion_search(ef)
+    rng = np.random.default_rng(5)
+    allowed = (rng.permutation(n)[: int(n * fraction)].astype(np.uint64) * 7 + 3)
+    want = ref.filtered_search(q, k, allowed, threads=16)
+    index = Index.restore(blob)
+    index.expansion_search = ef
+    got = index.filtered_search(q, k, allowed)
+    common.assert_same_results(want, (got.keys, got.distances, got.counts, index.last_computed, index.last_visited),
+                               f"filtered {fraction}")
+    if fraction:
+        assert np.isin(got.keys[got.distances == got.distances], allowed).all()
+    else:
+        assert (got.counts == 0).all()
+
+
+@pytest.mark.skipif(not common.have_reference(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("metric,scalar,d", [("cos", "f16", 128), ("ip", "bf16", 96), ("cos", "i8", 256), ("hamming", "b1", 256)])
+def test_f32_queries_are_cast_like_the_reference(metric, scalar, d):
+    """Queries arrive as f32 while the index stores another scalar kind: the host cast of the C ABI must equal
+    the reference's `cast_gt` (index_plugins.hpp:1105-1224) — here the reference casts the same f32 queries itself."""
+    from usearch_b200.index import Index
+    n, m, ef, k = 4000, 16, 64, 10
+    base, _ = common.make_collection(n, d, scalar, 8)
+    q32 = common.datagen.latent(100, d, seed=77, rank=16)
+    ref, blob = common.build_reference_blob(base, metric, scalar, d, m, threads=16)
+    ref.pin_metric(True)
+    ref.change_expansion_search(ef)
+    want = ref.filtered_search(q32, k, np.arange(n, dtype=np.uint64), threads=16)  # every key allowed
+    index = Index.restore(blob)
+    index.expansion_search = ef
+    got = index.search(q32, k, stats=True)
+    common.assert_same_results(want, (got.keys, got.distances, got.counts, index.last_computed, index.last_visited),
+                               f"f32 -> {scalar}")

@@ -298,6 +298,24 @@ size_t usearch_b200_search_many_stats(usearch_index_t index, void const* queries
     return total;
 }
 
+size_t usearch_b200_filtered_search_many(usearch_index_t index, void const* queries, size_t queries_count,
+                                         size_t queries_stride, usearch_scalar_kind_t query_kind, size_t count,
+                                         usearch_key_t const* allowed_keys, size_t allowed_count, usearch_key_t* keys,
+                                         usearch_distance_t* distances, size_t* counts, uint64_t* computed_distances,
+                                         uint64_t* visited_members, usearch_error_t* error) {
+    frozen_index_t* ix = as_index(index);
+    uint32_t qs = scalar_to_char(query_kind);
+    if (!qs) { set_error(error, "Unknown scalar kind!"); return 0; }
+    size_t total = 0;
+    if (char const* e = ix->search_host(queries, queries_count, queries_stride, qs, count, keys, count * 8, distances,
+                                        count * 4, counts, computed_distances, visited_members, &total, allowed_keys,
+                                        allowed_count, true)) {
+        set_error(error, e);
+        return 0;
+    }
+    return total;
+}
+
 void usearch_b200_search_many_device(usearch_index_t index, void const* queries, size_t queries_count, size_t queries_stride,
                                      size_t count, usearch_key_t* keys, usearch_distance_t* distances, uint32_t* counts,
                                      uint32_t* computed_distances, uint32_t* visited_members, void* cuda_stream,

@@ -79,6 +79,10 @@ struct search_args_t {
     uint32_t* out_computed = nullptr; /* may be NULL */
     uint32_t* out_visited = nullptr;  /* may be NULL */
     uint32_t* status = nullptr;
+    /* optional device-side predicate (filtered_search): one bit per slot, set = allowed. Applied exactly
+     * where the reference applies its predicate (index.hpp:4201, :4236-4240): a rejected member still
+     * enters `next` and is expanded, it just never enters `top`. */
+    uint32_t const* allow_bits = nullptr;
     /* scheduling + scratch */
     uint32_t* work_counter = nullptr;
     uint32_t* visited = nullptr; /* [warps x visited_cap] */

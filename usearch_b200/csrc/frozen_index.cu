@@ -62,6 +62,7 @@ frozen_index_t::~frozen_index_t() {
     phase_cycles.release();
     visited.release(); work_counter.release(); status.release(); counts.release(); computed.release();
     cycles.release(); retry_list.release(); heap_spill.release(); queries.release(); out_keys.release();
+    allowed_keys.release(); allow_bits.release();
     out_dists.release(); h_queries.release(); h_keys.release(); h_dists.release(); h_counts.release();
     h_computed.release(); h_cycles.release(); h_status.release();
 }
@@ -489,6 +490,7 @@ char const* frozen_index_t::search_device(void const* d_queries, size_t nq, size
     a.out_computed = d_computed;
     a.out_visited = d_cycles;
     a.status = status.ptr;
+    a.allow_bits = active_allow_bits;
     a.work_counter = work_counter.ptr;
     a.visited = visited.ptr;
     a.visited_cap = pl.visited_cap;
@@ -651,7 +653,8 @@ char const* cast_queries(uint32_t from, uint32_t to, size_t dims, uint8_t const*
 
 char const* frozen_index_t::search_host(void const* q, size_t nq, size_t stride, uint32_t query_scalar, size_t k,
                                         uint64_t* keys, size_t keys_stride, float* dists, size_t dists_stride,
-                                        size_t* counts, uint64_t* computed_out, uint64_t* cycles_out, size_t* total) {
+                                        size_t* counts, uint64_t* computed_out, uint64_t* cycles_out, size_t* total,
+                                        uint64_t const* allowed, size_t allowed_count, bool filtered) {
     if (total) *total = 0;
     if (!loaded) return "Index is empty: load a serialized index first";
     if (nq == 0 || k == 0) return nullptr;
@@ -674,6 +677,23 @@ char const* frozen_index_t::search_host(void const* q, size_t nq, size_t stride,
                                          h_queries.ptr, vs))
             return e;
         CU(cudaMemcpy2DAsync(queries.ptr, vs, h_queries.ptr, vs, bpv, nq, cudaMemcpyHostToDevice, stream));
+    }
+
+    /* filtered search: sort the allowed keys on the host, turn them into a bitmap over slots on the device */
+    struct reset_filter_t {
+        frozen_index_t* self;
+        ~reset_filter_t() { self->active_allow_bits = nullptr; }
+    } reset_filter{this};
+    if (filtered && size) {
+        std::vector<uint64_t> sorted(allowed, allowed + allowed_count);
+        std::sort(sorted.begin(), sorted.end());
+        if (char const* e = allowed_keys.reserve(std::max<size_t>(sorted.size(), 1))) return e;
+        if (char const* e = allow_bits.reserve((size + 31) / 32)) return e;
+        if (!sorted.empty())
+            CU(cudaMemcpyAsync(allowed_keys.ptr, sorted.data(), sorted.size() * 8, cudaMemcpyHostToDevice, stream));
+        CU(search_build_allow_bits(d, allowed_keys.ptr, (uint32_t)sorted.size(), allow_bits.ptr, stream));
+        CU(cudaStreamSynchronize(stream)); /* `sorted` is pageable host memory */
+        active_allow_bits = allow_bits.ptr;
     }
 
     bool const want_stats = computed_out || cycles_out;

@@ -27,6 +27,8 @@ int search_stage_slots(device_index_t const& ix);
 int search_lanes_per_vector(device_index_t const& ix);
 bool search_needs_norms(uint32_t metric, uint32_t scalar);
 cudaError_t search_compute_norms(device_index_t const& ix, float* norms, cudaStream_t stream);
+cudaError_t search_build_allow_bits(device_index_t const& ix, uint64_t const* allowed_sorted, uint32_t m, uint32_t* bits,
+                                    cudaStream_t stream);
 
 /* indexes up to this many slots track `visits` as a per-warp bitmap (512 KB at the limit) */
 constexpr uint64_t BITMAP_MAX_SLOTS = 1ull << 22;
@@ -114,6 +116,9 @@ struct frozen_index_t {
     device_buffer_t<uint32_t> visited, work_counter, status, counts, computed, cycles, retry_list;
     device_buffer_t<cand_t> heap_spill;
     device_buffer_t<uint8_t> queries;
+    device_buffer_t<uint64_t> allowed_keys; /* filtered search: sorted allowed keys and the bitmap built from them */
+    device_buffer_t<uint32_t> allow_bits;
+    uint32_t const* active_allow_bits = nullptr; /* set for the duration of one filtered call */
     device_buffer_t<uint64_t> out_keys;
     device_buffer_t<float> out_dists;
     pinned_buffer_t<uint8_t> h_queries;
@@ -142,7 +147,8 @@ struct frozen_index_t {
                               uint32_t* d_counts, uint32_t* d_computed, uint32_t* d_cycles, cudaStream_t stream);
     char const* search_host(void const* queries, size_t nq, size_t stride, uint32_t query_scalar, size_t k, uint64_t* keys,
                             size_t keys_stride, float* dists, size_t dists_stride, size_t* counts, uint64_t* computed,
-                            uint64_t* cycles, size_t* total);
+                            uint64_t* cycles, size_t* total, uint64_t const* allowed = nullptr, size_t allowed_count = 0,
+                            bool filtered = false);
 };
 
 /* host-side query casts (index_plugins.hpp:1105-1224) */

@@ -426,6 +426,14 @@ __device__ __forceinline__ void measure_list(device_index_t const& ix, search_ar
     }
 }
 
+/* The predicate of index_dense_gt::search_ (index_dense.hpp:2071-2083): not the free key, and — for a
+ * filtered search — accepted by the caller's predicate, here a bitmap over slots. */
+__device__ __forceinline__ bool slot_allowed(device_index_t const& ix, search_args_t const& a, uint32_t s) {
+    if (ix.deleted_bits && ((ix.deleted_bits[s >> 5] >> (s & 31)) & 1u)) return false;
+    if (a.allow_bits && !((a.allow_bits[s >> 5] >> (s & 31)) & 1u)) return false;
+    return true;
+}
+
 /* ---- one query ------------------------------------------------------------------------------ */
 
 template <class M, bool STAGED>
@@ -551,7 +559,7 @@ __device__ __forceinline__ void search_one(device_index_t const& ix, search_args
         uint32_t pre_node = EMPTY_SLOT, pre_s0 = EMPTY_SLOT, pre_s1 = EMPTY_SLOT; /* speculative row prefetch */
         PHASE(pc0)
         {
-            bool allowed = !ix.deleted_bits || !((ix.deleted_bits[closest >> 5] >> (closest & 31)) & 1u);
+            bool allowed = slot_allowed(ix, a, closest);
             if (allowed) {
                 if (topreg) {
                     if (lane == 0) { rtd[0] = radius; rts[0] = closest; }
@@ -667,7 +675,7 @@ __device__ __forceinline__ void search_one(device_index_t const& ix, search_args
                         heap.push(heap_size, cand_t{d, s}, lane);
                         heap_size += 1;
                         if (prof) { n_push += 1; max_heap = max(max_heap, heap_size); }
-                        bool allowed = !ix.deleted_bits || !((ix.deleted_bits[s >> 5] >> (s & 31)) & 1u);
+                        bool allowed = slot_allowed(ix, a, s);
                         if (allowed) {
                             if (topreg) {
                                 top_insert_reg(rtd, rts, top_size, ef, d, s, lane);
@@ -771,6 +779,32 @@ __global__ void __launch_bounds__(THREADS, STAGED ? 8 : 16) hnsw_search_kernel(_
         uint32_t qi = a.query_list ? a.query_list[item] : item;
         search_one<M, STAGED>(ix, a, qi, w, heap, visited, lane);
     }
+}
+
+/* ---- filtered search: allowed keys -> bitmap over slots -------------------------------------------- */
+
+__global__ void allow_bits_kernel(uint64_t const* keys, uint32_t n, uint64_t const* allowed_sorted, uint32_t m, uint32_t* bits) {
+    uint32_t const slot = blockIdx.x * blockDim.x + threadIdx.x;
+    bool hit = false;
+    if (slot < n) {
+        uint64_t const key = keys[slot];
+        uint32_t lo = 0, hi = m;
+        while (lo < hi) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (allowed_sorted[mid] < key) lo = mid + 1;
+            else hi = mid;
+        }
+        hit = lo < m && allowed_sorted[lo] == key;
+    }
+    uint32_t const word = __ballot_sync(0xffffffffu, hit);
+    if ((threadIdx.x & 31) == 0 && slot < n) bits[slot >> 5] = word;
+}
+
+cudaError_t search_build_allow_bits(device_index_t const& ix, uint64_t const* allowed_sorted, uint32_t m, uint32_t* bits,
+                                    cudaStream_t stream) {
+    if (!ix.n) return cudaSuccess;
+    allow_bits_kernel<<<(ix.n + 255) / 256, 256, 0, stream>>>(ix.keys, ix.n, allowed_sorted, m, bits);
+    return cudaGetLastError();
 }
 
 /* ---- freeze-time helper: squared norms in the metric's summation order -------------------------- */

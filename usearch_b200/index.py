@@ -48,6 +48,7 @@ EXPORTED_SYMBOLS = [
     "usearch_exact_search", "usearch_clear",
     # additive
     "usearch_search_many", "usearch_b200_search_many_device", "usearch_b200_search_many_stats",
+    "usearch_b200_filtered_search_many",
     "usearch_b200_profile_phases", "usearch_b200_device", "usearch_b200_kernel_launches", "usearch_b200_last_kernel_ms",
     "usearch_b200_bytes_per_vector", "usearch_b200_max_level",
 ]
@@ -95,6 +96,10 @@ def load_library() -> C.CDLL:
     lib.usearch_b200_search_many_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t,
                                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                     C.c_void_p, err]
+    lib.usearch_b200_filtered_search_many.restype = C.c_size_t
+    lib.usearch_b200_filtered_search_many.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int,
+                                                      C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                                      C.c_void_p, C.c_void_p, C.c_void_p, err]
     lib.usearch_b200_profile_phases.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.usearch_b200_device.argtypes = [C.c_void_p]
     lib.usearch_b200_kernel_launches.restype = C.c_uint64
@@ -284,8 +289,18 @@ class Index:
             return "i8"
         return kind
 
-    def search(self, vectors: np.ndarray, count: int = 10, *, stats: bool = False) -> Union[Matches, BatchMatches]:
-        """1-D input → :class:`Matches`; 2-D input → :class:`BatchMatches` (index.py:191-231)."""
+    def filtered_search(self, vectors: np.ndarray, count: int, allowed_keys) -> Union[Matches, BatchMatches]:
+        """`filtered_search` (index_dense.hpp:774-779) for the predicate "key in allowed_keys"."""
+        return self.search(vectors, count, stats=True, _allowed=np.ascontiguousarray(allowed_keys, dtype=np.uint64))
+
+    def search(self, vectors: np.ndarray, count: int = 10, *, stats: bool = False, threads: int = 0, exact: bool = False,
+               log=False, progress=None, _allowed: Optional[np.ndarray] = None) -> Union[Matches, BatchMatches]:
+        """1-D input → :class:`Matches`; 2-D input → :class:`BatchMatches` (index.py:191-231).
+
+        `threads`, `log` and `progress` are accepted for signature compatibility with index.py:700-748 and
+        ignored (one kernel launch serves the whole batch); `exact=True` is not offloaded."""
+        if exact:
+            raise NotImplementedError("exact (brute-force) search is not offloaded: use the host library")
         vectors = np.asarray(vectors)
         single = vectors.ndim == 1
         if single:
@@ -304,7 +319,18 @@ class Index:
         counts = np.zeros(nq, dtype=np.uint64)
         err = C.c_char_p()
         vm = cd = 0
-        if stats:
+        if _allowed is not None:
+            computed = np.zeros(nq, dtype=np.uint64)
+            visited = np.zeros(nq, dtype=np.uint64)
+            self._lib.usearch_b200_filtered_search_many(
+                self._h, vectors.ctypes.data_as(C.c_void_p), nq, vectors.strides[0], SCALAR_KIND[kind], count,
+                _allowed.ctypes.data_as(C.c_void_p), _allowed.size, keys.ctypes.data_as(C.c_void_p),
+                distances.ctypes.data_as(C.c_void_p), counts.ctypes.data_as(C.c_void_p),
+                computed.ctypes.data_as(C.c_void_p), visited.ctypes.data_as(C.c_void_p), C.byref(err))
+            _raise(err)
+            self.last_computed, self.last_visited = computed, visited
+            vm, cd = int(visited.sum()), int(computed.sum())
+        elif stats:
             computed = np.zeros(nq, dtype=np.uint64)
             visited = np.zeros(nq, dtype=np.uint64)
             self._lib.usearch_b200_search_many_stats(
