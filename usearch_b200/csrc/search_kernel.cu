@@ -247,34 +247,34 @@ __device__ __forceinline__ void top_insert(float* td, uint32_t* ts, uint32_t& si
 }
 
 /*
- *  Register-resident `top` for ef <= 256: lane l holds elements l, l+32, ... (TOP_E chunks). The
- *  same sorted_buffer_gt::insert semantics, but the right-shift is done with shuffles: element i
- *  receives element i-1, which lives in the neighbouring lane (or in lane 31 of the previous chunk).
+ *  Register-resident `top` for ef <= 256, BLOCKED layout: lane l holds elements 8l .. 8l+7. The same
+ *  sorted_buffer_gt::insert semantics (index.hpp:928-939); the right-shift costs one shuffle per array:
+ *  element g receives element g-1, which is the previous register of the same lane or register 7 of
+ *  the lane below.
  */
 constexpr int TOP_E = 8;
 
 __device__ __forceinline__ void top_insert_reg(float (&td)[TOP_E], uint32_t (&ts)[TOP_E], uint32_t& size, uint32_t limit,
                                                float d, uint32_t s, int lane) {
+    uint32_t const g0 = (uint32_t)lane * TOP_E;
     uint32_t mine = 0; /* lower_bound: number of stored distances strictly below d */
 #pragma unroll
-    for (int c = 0; c < TOP_E; ++c) mine += ((uint32_t)(c * 32 + lane) < size && td[c] < d) ? 1u : 0u;
+    for (int j = 0; j < TOP_E; ++j) mine += (g0 + j < size && td[j] < d) ? 1u : 0u;
     uint32_t const pos = __reduce_add_sync(0xffffffffu, mine);
     if (pos == limit) return;
     bool const full = size == limit;
     uint32_t const hi = size - (full ? 1u : 0u); /* old [pos, hi) becomes new (pos, hi] */
+    float const up_d = __shfl_up_sync(0xffffffffu, td[TOP_E - 1], 1);
+    uint32_t const up_s = __shfl_up_sync(0xffffffffu, ts[TOP_E - 1], 1);
 #pragma unroll
-    for (int c = TOP_E - 1; c >= 0; --c) {
-        if (c * 32 <= (int)hi && (c + 1) * 32 > (int)pos) { /* chunk intersects [pos, hi] */
-            float pd = __shfl_up_sync(0xffffffffu, td[c], 1);
-            uint32_t ps = __shfl_up_sync(0xffffffffu, ts[c], 1);
-            if (c > 0) {
-                float cd = __shfl_sync(0xffffffffu, td[c - 1 < 0 ? 0 : c - 1], 31);
-                uint32_t cs = __shfl_sync(0xffffffffu, ts[c - 1 < 0 ? 0 : c - 1], 31);
-                if (lane == 0) { pd = cd; ps = cs; }
-            }
-            uint32_t const i = (uint32_t)(c * 32 + lane);
-            if (i > pos && i <= hi) { td[c] = pd; ts[c] = ps; }
-            else if (i == pos) { td[c] = d; ts[c] = s; }
+    for (int j = TOP_E - 1; j >= 0; --j) {
+        uint32_t const g = g0 + (uint32_t)j;
+        if (g > pos && g <= hi) {
+            td[j] = j ? td[j > 0 ? j - 1 : 0] : up_d;
+            ts[j] = j ? ts[j > 0 ? j - 1 : 0] : up_s;
+        } else if (g == pos) {
+            td[j] = d;
+            ts[j] = s;
         }
     }
     size += full ? 0u : 1u;
@@ -282,12 +282,12 @@ __device__ __forceinline__ void top_insert_reg(float (&td)[TOP_E], uint32_t (&ts
 
 /* distance of the last (worst) element: sorted_buffer_gt::top() (index.hpp:891) */
 __device__ __forceinline__ float top_back_reg(float const (&td)[TOP_E], uint32_t size) {
-    uint32_t const i = size - 1, cc = i >> 5;
-    float sel = 0.f;
+    uint32_t const i = size - 1, r = i & (TOP_E - 1);
+    float sel = td[0];
 #pragma unroll
-    for (int c = 0; c < TOP_E; ++c)
-        if ((uint32_t)c == cc) sel = td[c];
-    return __shfl_sync(0xffffffffu, sel, (int)(i & 31));
+    for (int j = 1; j < TOP_E; ++j)
+        if ((uint32_t)j == r) sel = td[j];
+    return __shfl_sync(0xffffffffu, sel, (int)(i / TOP_E));
 }
 
 /* ---- per-warp view of shared memory and scratch ---------------------------------------------- */
@@ -349,14 +349,28 @@ __device__ __forceinline__ void measure_staged(device_index_t const& ix, search_
     uint32_t const chunks = ix.chunks16, bytes = (uint32_t)ix.vec_stride;
     uint32_t const nsets = a.stage_sets; /* 1: fetch-then-reduce; 2: the next pass lands while this one is reduced */
     uint32_t const npass = (ncand + VPP - 1) / VPP;
-    /* pass p = candidates [p*VPP, p*VPP+VPP) -> slot set p % nsets; lane l < cnt issues the copy of slot l */
+    /* pass p = candidates [p*VPP, p*VPP+VPP) -> slot set p % nsets, ONE mbarrier per set. `cp.async.bulk`
+     * takes its operands in uniform registers, so a per-lane issue is serialised by the compiler with an
+     * ELECT loop (~45 cycles per copy). Instead every lane reads its candidate once, the slot numbers are
+     * made warp-uniform with shuffles and lane 0 issues the copies back to back. */
     auto issue = [&](uint32_t p) {
-        uint32_t const base = p * VPP, cnt = min((uint32_t)VPP, ncand - base);
-        if (lane < (int)cnt) {
-            uint32_t const slot = w.cand_s[base + lane], sl = (p % nsets) * VPP + lane;
-            uint32_t const bar = w.bars_addr + 8u * sl;
-            mbar_expect_tx(bar, bytes);
-            bulk_copy_g2s(w.stage_addr + sl * a.stage_stride, ix.vectors + (size_t)slot * ix.vec_stride, bytes, bar);
+        uint32_t const base = p * VPP, cnt = min((uint32_t)VPP, ncand - base), set = p % nsets;
+        uint32_t const my_slot = (uint32_t)lane < cnt ? w.cand_s[base + lane] : 0u;
+        uint32_t const bar = w.bars_addr + 8u * set;
+        if (lane == 0) mbar_expect_tx(bar, cnt * bytes);
+        if constexpr (VPP <= 8) {
+#pragma unroll
+            for (int i = 0; i < VPP; ++i) {
+                uint32_t const slot = __shfl_sync(0xffffffffu, my_slot, i);
+                if (lane == 0 && (uint32_t)i < cnt)
+                    bulk_copy_g2s(w.stage_addr + (set * VPP + i) * a.stage_stride, ix.vectors + (size_t)slot * ix.vec_stride, bytes, bar);
+            }
+        } else {
+            for (uint32_t i = 0; i < cnt; ++i) {
+                uint32_t const slot = __shfl_sync(0xffffffffu, my_slot, (int)i);
+                if (lane == 0)
+                    bulk_copy_g2s(w.stage_addr + (set * VPP + i) * a.stage_stride, ix.vectors + (size_t)slot * ix.vec_stride, bytes, bar);
+            }
         }
     };
     issue(0);
@@ -370,12 +384,12 @@ __device__ __forceinline__ void measure_staged(device_index_t const& ix, search_
         M::init(acc);
         if (a.phase_cycles) { /* introspection only: attribute the wait for the slowest slot to `vector_wait` */
             long long t = clock64();
-            if (act) mbar_wait(w.bars_addr + 8u * sl, (w.phase >> sl) & 1u);
+            if (act) mbar_wait(w.bars_addr + 8u * (p % nsets), (w.phase >> (p % nsets)) & 1u);
             __syncwarp();
             w.t_wait += (uint32_t)(clock64() - t);
         }
         if (act) {
-            if (!a.phase_cycles) mbar_wait(w.bars_addr + 8u * sl, (w.phase >> sl) & 1u);
+            if (!a.phase_cycles) mbar_wait(w.bars_addr + 8u * (p % nsets), (w.phase >> (p % nsets)) & 1u);
             /* 4 steps per iteration, the next iteration's 8 shared-memory loads issued before this one's
              * math: with one warp per scheduler nothing else hides the LDS latency */
             uint32_t j = sub;
@@ -402,7 +416,7 @@ __device__ __forceinline__ void measure_staged(device_index_t const& ix, search_
         }
         float d = M::finish(acc, qc);
         if (act && sub == 0) w.cand_d[base + g] = d;
-        w.phase ^= (cnt >= 32u ? 0xFFFFFFFFu : (1u << cnt) - 1u) << ((p % nsets) * VPP);
+        w.phase ^= 1u << (p % nsets); /* one parity bit per set */
         __syncwarp(); /* every lane is done with this set before it is refilled */
         if (p + nsets < npass) issue(p + nsets);
     }
@@ -699,14 +713,14 @@ __device__ __forceinline__ void search_one(device_index_t const& ix, search_args
     uint32_t count = top_size < k ? top_size : k;
     if (topreg) {
 #pragma unroll
-        for (int c = 0; c < TOP_E; ++c) {
-            uint32_t const i = (uint32_t)(c * 32 + lane);
-            if (c * 32 < (int)k && i < k) {
+        for (int j = 0; j < TOP_E; ++j) {
+            uint32_t const i = (uint32_t)lane * TOP_E + (uint32_t)j;
+            if (i < k) {
                 uint64_t key = 0;
                 uint32_t bits = SNAN_BITS;
                 if (i < count) {
-                    key = ix.keys[rts[c]];
-                    bits = __float_as_uint(rtd[c]);
+                    key = ix.keys[rts[j]];
+                    bits = __float_as_uint(rtd[j]);
                 }
                 a.out_keys[(size_t)qi * k + i] = key;
                 reinterpret_cast<uint32_t*>(a.out_dists)[(size_t)qi * k + i] = bits;
