@@ -349,16 +349,21 @@ __device__ __forceinline__ void measure_staged(device_index_t const& ix, search_
     uint32_t const chunks = ix.chunks16, bytes = (uint32_t)ix.vec_stride;
     uint32_t const nsets = a.stage_sets; /* 1: fetch-then-reduce; 2: the next pass lands while this one is reduced */
     uint32_t const npass = (ncand + VPP - 1) / VPP;
-    /* pass p = candidates [p*VPP, p*VPP+VPP) -> slot set p % nsets, ONE mbarrier per set. `cp.async.bulk`
-     * takes its operands in uniform registers, so a per-lane issue is serialised by the compiler with an
-     * ELECT loop (~45 cycles per copy). Instead every lane reads its candidate once, the slot numbers are
-     * made warp-uniform with shuffles and lane 0 issues the copies back to back. */
+    /* pass p = candidates [p*VPP, p*VPP+VPP) -> slot set p % nsets, ONE mbarrier per set (lane 0 arms it
+     * with the byte count of the whole pass). `cp.async.bulk` takes its operands in uniform registers, so
+     * the per-lane issue below is serialised by the compiler with an ELECT loop; the alternative — lane 0
+     * issuing all copies back to back from shuffled slot numbers — measured 7 % slower end to end and is
+     * kept only as a tuning knob (`issue_per_lane == 0`). */
     auto issue = [&](uint32_t p) {
         uint32_t const base = p * VPP, cnt = min((uint32_t)VPP, ncand - base), set = p % nsets;
         uint32_t const my_slot = (uint32_t)lane < cnt ? w.cand_s[base + lane] : 0u;
         uint32_t const bar = w.bars_addr + 8u * set;
         if (lane == 0) mbar_expect_tx(bar, cnt * bytes);
-        if constexpr (VPP <= 8) {
+        __syncwarp();
+        if (a.issue_per_lane) { /* every lane issues its own copy (the compiler serialises them with ELECT) */
+            if ((uint32_t)lane < cnt)
+                bulk_copy_g2s(w.stage_addr + (set * VPP + lane) * a.stage_stride, ix.vectors + (size_t)my_slot * ix.vec_stride, bytes, bar);
+        } else if constexpr (VPP <= 8) {
 #pragma unroll
             for (int i = 0; i < VPP; ++i) {
                 uint32_t const slot = __shfl_sync(0xffffffffu, my_slot, i);
