@@ -33,7 +33,9 @@ def main():
                            expansion_add=128, ef=args.ef, batch=args.batch, k=10, rank_latent=16)
     import torch
     from usearch_b200.index import Index
-    keys, base, blob, path, info = bench.get_index_blob(a, 0, 1, bench.host_threads())
+    path = os.path.join(bench.CACHE, f"index_{bench.shard_key(a, 0, 1)}.usearch")
+    if not os.path.exists(path):  # build once per gpurun call; later invocations skip the 12 s of data generation
+        bench.get_index_blob(a, 0, 1, bench.host_threads())
     index = Index.restore(path)
     index.expansion_search = a.ef
     B, k = a.batch, a.k

@@ -389,18 +389,34 @@ char const* frozen_index_t::plan(uint32_t k, uint32_t visited_cap_override, laun
     off = round_up(off, 128);
     pl.off_stage = off;
     int const slots = search_stage_slots(d); /* slots of one set: 32 / LPV */
-    /* slot stride = 16*LPV mod 128 bytes: the lanes of a quarter-warp then read disjoint banks */
-    pl.stage_stride = slots ? round_up((uint32_t)d.vec_stride, 128) + 16u * (uint32_t)search_lanes_per_vector(d) : 0;
+    uint32_t const lpv = (uint32_t)search_lanes_per_vector(d);
     /* an SM has 228 KB of shared memory and charges 1 KB per resident CTA on top of its request */
     size_t const smem_sm = 228 * 1024, cta_tax = 1024, smem_cta_max = 227 * 1024;
     uint32_t const min_heap = 128 * 8;
-    /* double-buffer the TMA slots when at least 4 warps per SM still fit */
     static int const forced_sets = [] { char const* v = std::getenv("USEARCH_B200_STAGE_SETS"); return v ? std::atoi(v) : 0; }();
+    static int const forced_segs = [] { char const* v = std::getenv("USEARCH_B200_STAGE_SEGMENTS"); return v ? std::atoi(v) : 0; }();
     pl.stage_sets = 1;
+    pl.stage_segments = 1;
+    pl.stage_seg_chunks = d.chunks16;
+    pl.stage_stride = 0;
     if (slots) {
+        /* Long vectors CAN be fetched as two half-size segments (USEARCH_B200_STAGE_SEGMENTS=2): twice the copies
+         * for almost twice the resident warps (7 instead of 4 per SM at 768 x f32). Measured on B200 it is a wash
+         * (9.90 ms vs 9.79 ms per 4096-query batch): the kernel is limited by shared-memory traffic per vector,
+         * not by thread-level parallelism, so whole-vector slots stay the default. The split point is a multiple
+         * of 4*LPV chunks so that both halves run the unrolled loop. */
+        bool const can_split = lpv == 4 && d.chunks16 >= 64;
+        uint32_t segs = 1u;
+        if (forced_segs == 2 && can_split) segs = 2u;
+        pl.stage_segments = segs;
+        pl.stage_seg_chunks = segs == 1 ? d.chunks16 : round_up((d.chunks16 + 1) / 2, 4 * lpv);
+        /* slot stride = 16*LPV mod 128 bytes: the lanes of a quarter-warp then read disjoint banks */
+        pl.stage_stride = round_up(pl.stage_seg_chunks * 16, 128) + 16u * lpv;
+        /* double-buffer the slots when at least 4 warps per SM still fit */
         size_t const two = off + 2 * (size_t)slots * pl.stage_stride + min_heap + cta_tax;
         pl.stage_sets = (forced_sets == 1 || forced_sets == 2) ? (uint32_t)forced_sets : (smem_sm / two >= 4 ? 2u : 1u);
-        if (slots > 16) pl.stage_sets = 1; /* one parity bit per slot in a 32-bit word */
+        if (slots > 16) pl.stage_sets = 1; /* one lane per vector: 32 slots in a single set */
+        if (segs == 2) pl.stage_sets = 2;  /* the two halves of a pass alternate between the two sets */
     }
     off += (uint32_t)slots * pl.stage_sets * pl.stage_stride;
     pl.off_heap = off;
@@ -503,6 +519,8 @@ char const* frozen_index_t::search_device(void const* d_queries, size_t nq, size
     a.off_cand_d = pl.off_cand_d; a.off_heap = pl.off_heap;
     a.off_bars = pl.off_bars; a.off_stage = pl.off_stage; a.stage_stride = pl.stage_stride;
     a.stage_sets = pl.stage_sets;
+    a.stage_segments = pl.stage_segments;
+    a.stage_seg_chunks = pl.stage_seg_chunks;
     /* measured on B200 (1M x 768 f32): per-lane issue 9.67 ms, single-lane back-to-back issue 10.33 ms */
     static int const issue_per_lane = [] { char const* v = std::getenv("USEARCH_B200_ISSUE_PER_LANE"); return v ? std::atoi(v) : 1; }();
     a.issue_per_lane = (uint32_t)issue_per_lane;

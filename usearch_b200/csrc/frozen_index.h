@@ -39,7 +39,7 @@ struct launch_plan_t {
     bool maxed = false; /* growing the scratch any further cannot help */
     size_t visited_words_per_warp() const { return visited_bitmap_words ? visited_bitmap_words : visited_cap; }
     uint32_t smem_per_warp = 0, off_top_d = 0, off_top_s = 0, off_cand_s = 0, off_cand_d = 0, off_heap = 0;
-    uint32_t off_bars = 0, off_stage = 0, stage_stride = 0, stage_sets = 1;
+    uint32_t off_bars = 0, off_stage = 0, stage_stride = 0, stage_sets = 1, stage_segments = 1, stage_seg_chunks = 0;
     int blocks = 0;
     uint32_t warps_per_sm_target = 0;
     size_t smem_per_block = 0;

@@ -340,69 +340,77 @@ __device__ __noinline__ void measure_direct(device_index_t const& ix, warp_ctx_t
     __syncwarp();
 }
 
-/* STAGED: one TMA bulk copy per candidate vector into a shared-memory slot, then LPV lanes per slot. */
+/*
+ *  STAGED: TMA bulk copies (cp.async.bulk, UBLKCP) land candidate vectors in shared-memory slots, LPV lanes
+ *  then reduce each slot in the reference's summation order.
+ *
+ *  A vector may be fetched in `segs` SEGMENTS (1 or 2 copies of seg_chunks*16 bytes): with half-size
+ *  slots almost twice as many warps fit on an SM (7 instead of 4 at 768 x f32), and with one warp per
+ *  scheduler it is thread-level parallelism, not bandwidth, that the kernel is short of. The unit of
+ *  work is a "segment pass" sp = pass * segs + h: segment h of candidates [pass*VPP, pass*VPP+VPP) goes to
+ *  slot set sp % nsets, one mbarrier per set; the accumulators live across the segments of a pass, so
+ *  the order of the fma chain is untouched.
+ */
 template <class M>
 __device__ __forceinline__ void measure_staged(device_index_t const& ix, search_args_t const& a, warp_ctx_t& w,
                                                typename M::qconst_t qc, uint32_t ncand, int lane) {
     constexpr int LPV = M::LPV, VPP = 32 / LPV;
     int const g = lane / LPV, sub = lane % LPV;
-    uint32_t const chunks = ix.chunks16, bytes = (uint32_t)ix.vec_stride;
-    uint32_t const nsets = a.stage_sets; /* 1: fetch-then-reduce; 2: the next pass lands while this one is reduced */
-    uint32_t const npass = (ncand + VPP - 1) / VPP;
-    /* pass p = candidates [p*VPP, p*VPP+VPP) -> slot set p % nsets, ONE mbarrier per set (lane 0 arms it
-     * with the byte count of the whole pass). `cp.async.bulk` takes its operands in uniform registers, so
-     * the per-lane issue below is serialised by the compiler with an ELECT loop; the alternative — lane 0
-     * issuing all copies back to back from shuffled slot numbers — measured 7 % slower end to end and is
-     * kept only as a tuning knob (`issue_per_lane == 0`). */
-    auto issue = [&](uint32_t p) {
-        uint32_t const base = p * VPP, cnt = min((uint32_t)VPP, ncand - base), set = p % nsets;
+    uint32_t const chunks = ix.chunks16;
+    uint32_t const nsets = a.stage_sets; /* 1: fetch-then-reduce; 2: the next segment pass lands during the math */
+    uint32_t const segs = a.stage_segments, seg_chunks = a.stage_seg_chunks;
+    uint32_t const nsp = ((ncand + VPP - 1) / VPP) * segs;
+    /* `cp.async.bulk` takes uniform-register operands, so the per-lane issue is serialised by the compiler
+     * with an ELECT loop; lane 0 issuing all copies back to back measured 7 % slower end to end and is kept
+     * only as a tuning knob (`issue_per_lane == 0`). */
+    auto issue = [&](uint32_t sp) {
+        uint32_t const pass = sp / segs, h = sp - pass * segs;
+        uint32_t const base = pass * VPP, cnt = min((uint32_t)VPP, ncand - base), set = sp % nsets;
+        uint32_t const c0 = h * seg_chunks, bytes = (min(chunks, c0 + seg_chunks) - c0) * 16u;
         uint32_t const my_slot = (uint32_t)lane < cnt ? w.cand_s[base + lane] : 0u;
         uint32_t const bar = w.bars_addr + 8u * set;
         if (lane == 0) mbar_expect_tx(bar, cnt * bytes);
         __syncwarp();
-        if (a.issue_per_lane) { /* every lane issues its own copy (the compiler serialises them with ELECT) */
+        if (a.issue_per_lane) {
             if ((uint32_t)lane < cnt)
-                bulk_copy_g2s(w.stage_addr + (set * VPP + lane) * a.stage_stride, ix.vectors + (size_t)my_slot * ix.vec_stride, bytes, bar);
-        } else if constexpr (VPP <= 8) {
-#pragma unroll
-            for (int i = 0; i < VPP; ++i) {
-                uint32_t const slot = __shfl_sync(0xffffffffu, my_slot, i);
-                if (lane == 0 && (uint32_t)i < cnt)
-                    bulk_copy_g2s(w.stage_addr + (set * VPP + i) * a.stage_stride, ix.vectors + (size_t)slot * ix.vec_stride, bytes, bar);
-            }
+                bulk_copy_g2s(w.stage_addr + (set * VPP + lane) * a.stage_stride,
+                              ix.vectors + (size_t)my_slot * ix.vec_stride + (size_t)c0 * 16u, bytes, bar);
         } else {
             for (uint32_t i = 0; i < cnt; ++i) {
                 uint32_t const slot = __shfl_sync(0xffffffffu, my_slot, (int)i);
                 if (lane == 0)
-                    bulk_copy_g2s(w.stage_addr + (set * VPP + i) * a.stage_stride, ix.vectors + (size_t)slot * ix.vec_stride, bytes, bar);
+                    bulk_copy_g2s(w.stage_addr + (set * VPP + i) * a.stage_stride,
+                                  ix.vectors + (size_t)slot * ix.vec_stride + (size_t)c0 * 16u, bytes, bar);
             }
         }
     };
     issue(0);
-    if (nsets > 1 && npass > 1) issue(1);
-    for (uint32_t p = 0; p < npass; ++p) {
-        uint32_t const base = p * VPP, cnt = min((uint32_t)VPP, ncand - base);
-        uint32_t const sl = (p % nsets) * VPP + g;
-        uint4 const* buf = reinterpret_cast<uint4 const*>(w.stage + (size_t)sl * a.stage_stride);
+    if (nsets > 1 && nsp > 1) issue(1);
+    typename M::acc_t acc;
+    M::init(acc);
+    for (uint32_t sp = 0; sp < nsp; ++sp) {
+        uint32_t const pass = sp / segs, h = sp - pass * segs;
+        uint32_t const base = pass * VPP, cnt = min((uint32_t)VPP, ncand - base), set = sp % nsets;
+        uint32_t const c0 = h * seg_chunks, c1 = min(chunks, c0 + seg_chunks);
+        /* chunk j of the vector sits at slot offset (j - c0) * 16 */
+        uint4 const* buf = reinterpret_cast<uint4 const*>(w.stage + (size_t)(set * VPP + g) * a.stage_stride) - c0;
         bool const act = (uint32_t)g < cnt;
-        typename M::acc_t acc;
-        M::init(acc);
+        if (h == 0) M::init(acc);
         if (a.phase_cycles) { /* introspection only: attribute the wait for the slowest slot to `vector_wait` */
             long long t = clock64();
-            if (act) mbar_wait(w.bars_addr + 8u * (p % nsets), (w.phase >> (p % nsets)) & 1u);
+            if (act) mbar_wait(w.bars_addr + 8u * set, (w.phase >> set) & 1u);
             __syncwarp();
             w.t_wait += (uint32_t)(clock64() - t);
         }
         if (act) {
-            if (!a.phase_cycles) mbar_wait(w.bars_addr + 8u * (p % nsets), (w.phase >> (p % nsets)) & 1u);
-            /* 4 steps per iteration, the next iteration's 8 shared-memory loads issued before this one's
-             * math: with one warp per scheduler nothing else hides the LDS latency */
-            uint32_t j = sub;
-            if (j + 3 * LPV < chunks) {
+            if (!a.phase_cycles) mbar_wait(w.bars_addr + 8u * set, (w.phase >> set) & 1u);
+            /* 4 steps per iteration, the next iteration's 8 shared-memory loads issued before this one's math */
+            uint32_t j = c0 + sub;
+            if (j + 3 * LPV < c1) {
                 uint4 b0 = buf[j], b1 = buf[j + LPV], b2 = buf[j + 2 * LPV], b3 = buf[j + 3 * LPV];
                 uint4 q0 = w.q4[j], q1 = w.q4[j + LPV], q2 = w.q4[j + 2 * LPV], q3 = w.q4[j + 3 * LPV];
                 j += 4 * LPV;
-                for (; j + 3 * LPV < chunks; j += 4 * LPV) {
+                for (; j + 3 * LPV < c1; j += 4 * LPV) {
                     uint4 nb0 = buf[j], nb1 = buf[j + LPV], nb2 = buf[j + 2 * LPV], nb3 = buf[j + 3 * LPV];
                     uint4 nq0 = w.q4[j], nq1 = w.q4[j + LPV], nq2 = w.q4[j + 2 * LPV], nq3 = w.q4[j + 3 * LPV];
                     M::step(acc, b0, q0);
@@ -417,13 +425,15 @@ __device__ __forceinline__ void measure_staged(device_index_t const& ix, search_
                 M::step(acc, b2, q2);
                 M::step(acc, b3, q3);
             }
-            for (; j < chunks; j += LPV) M::step(acc, buf[j], w.q4[j]);
+            for (; j < c1; j += LPV) M::step(acc, buf[j], w.q4[j]);
         }
-        float d = M::finish(acc, qc);
-        if (act && sub == 0) w.cand_d[base + g] = d;
-        w.phase ^= 1u << (p % nsets); /* one parity bit per set */
-        __syncwarp(); /* every lane is done with this set before it is refilled */
-        if (p + nsets < npass) issue(p + nsets);
+        if (h + 1 == segs) { /* last segment of the pass: horizontal reduce (warp-wide shuffles: every lane) */
+            float d = M::finish(acc, qc);
+            if (act && sub == 0) w.cand_d[base + g] = d;
+        }
+        w.phase ^= 1u << set; /* one parity bit per set */
+        __syncwarp();         /* every lane is done with this set before it is refilled */
+        if (sp + nsets < nsp) issue(sp + nsets);
     }
 }
 
