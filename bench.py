@@ -346,6 +346,7 @@ def run_b200_arm(a):
         alg_bytes.append((D, H))
         if first_found is None:
             first_found = (out_k.clone(), cnt_dev.clone())
+            first_counters = (comp_dev.cpu().numpy().astype(np.uint64), vis_dev.cpu().numpy().astype(np.uint64))
     ev1.record(stream)
     barrier()
     launches = index.kernel_launches - launches0
@@ -415,6 +416,15 @@ def run_b200_arm(a):
                "sample": f"{sample} queries of the same workload in {dt_cpu:.1f} s, reference -O3 -ffast-math -march=native, SimSIMD {ref.isa_name}",
                "computed_distances_per_query": round(float(res_cpu[3].mean()), 1),
                "visited_members_per_query": round(float(res_cpu[4].mean()), 1)}
+        # full-size parity property: the first timed batch, GPU vs the reference's NATIVE SimSIMD kernels on the
+        # same graph (cosine differs by <= 1 ULP from the pinned arithmetic, so near-ties may swap)
+        lo, hi = W * B, (W + 1) * B
+        if sample >= hi:
+            gpu_keys = found_k.cpu().numpy().astype(np.uint64)
+            same_rows = (res_cpu[0][lo:hi] == gpu_keys).all(axis=1)
+            cpu["gpu_rows_with_identical_labels"] = round(float(same_rows.mean()), 6)
+            cpu["gpu_counters_identical"] = bool(np.array_equal(res_cpu[3][lo:hi], first_counters[0]) and
+                                                 np.array_equal(res_cpu[4][lo:hi], first_counters[1]))
         del ref
 
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
