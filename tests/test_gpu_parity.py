@@ -56,10 +56,12 @@ def test_search_matches_reference(metric, scalar, n, d, m, ef, k, nq):
     assert index.kernel_launches >= 1
 
 
-@pytest.mark.parametrize("mode", ["hash", "bitmap"])
-def test_visited_modes_and_scratch_retry(mode):
-    """Both `visits` implementations are exact; in hash mode i.i.d. data overflows the default table for
-    some queries, which exercises the flag-and-retry path (frozen_index_t::search_device)."""
+@pytest.mark.parametrize("mode,shrink", [("hash", 64), ("bitmap", 64), ("bitmap_log", 64), ("bitmap_log", 1)])
+def test_visited_modes_and_scratch_retry(mode, shrink):
+    """All `visits` implementations are exact: open-addressing table (undersized on purpose: flag-and-retry path of
+    frozen_index_t::search_device), bitmap wiped per query, bitmap cleaned through the per-query log of set bits
+    (with a 64x undersized log: fall back to a full wipe). 8192 queries: every warp serves several in a row, so a
+    bitmap left dirty by one query would corrupt the next."""
     import os
     import subprocess
     import sys
@@ -68,7 +70,7 @@ def test_visited_modes_and_scratch_retry(mode):
         "import numpy as np, common\n"
         "from oracle import bindings\n"
         "from usearch_b200.index import Index\n"
-        "base, q = common.make_collection(30000, 64, 'f32', 512, iid=True)\n"
+        "base, q = common.make_collection(30000, 64, 'f32', 8192, iid=True)\n"
         "ref, blob = common.build_reference_blob(base, 'l2sq', 'f32', 64, 16, threads=16)\n"
         "want = bindings.PortIndex(blob, 64).search(q, 10, threads=16)\n"
         "index = Index.restore(blob); index.expansion_search = 64\n"
@@ -76,7 +78,7 @@ def test_visited_modes_and_scratch_retry(mode):
         "common.assert_same_results(want, (got.keys, got.distances, got.counts, index.last_computed, index.last_visited), 'mode')\n"
         "print('launches', index.kernel_launches, 'maxD', int(want[3].max()))\n"
     ) % (common.ROOT, os.path.join(common.ROOT, "tests"))
-    env = dict(os.environ, USEARCH_B200_VISITED=mode, USEARCH_B200_SCRATCH_SHRINK="64")
+    env = dict(os.environ, USEARCH_B200_VISITED=mode, USEARCH_B200_SCRATCH_SHRINK=str(shrink))
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     launches = int(out.stdout.split("launches")[1].split()[0])

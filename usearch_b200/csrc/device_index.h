@@ -90,6 +90,11 @@ struct search_args_t {
     /* BITMAP mode (visited_bitmap_words != 0): `visited` holds one bit per slot, words per warp
      * (multiple of 4); one atomicOr per neighbour answers "seen before?" in a single round trip */
     uint32_t visited_bitmap_words = 0;
+    /* Large bitmaps are not wiped per query: every slot whose bit gets set is appended to a per-warp log and
+     * exactly those words are zeroed when the query ends (the bitmap is all-zero between queries). A log that
+     * overflows falls back to a full wipe of that query's bitmap. NULL = wipe at the start of every query. */
+    uint32_t* visit_log = nullptr; /* [warps x visit_log_cap] */
+    uint32_t visit_log_cap = 0;
     cand_t* heap_spill = nullptr; /* [warps x heap_spill_cap] */
     uint32_t heap_spill_cap = 0;
     uint32_t heap_smem_cap = 0;

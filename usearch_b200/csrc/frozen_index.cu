@@ -60,6 +60,7 @@ frozen_index_t::~frozen_index_t() {
     if (ev_begin) cudaEventDestroy(ev_begin);
     if (ev_end) cudaEventDestroy(ev_end);
     phase_cycles.release();
+    visit_log.release();
     visited.release(); work_counter.release(); status.release(); counts.release(); computed.release();
     cycles.release(); retry_list.release(); heap_spill.release(); queries.release(); out_keys.release();
     allowed_keys.release(); allow_bits.release();
@@ -437,24 +438,30 @@ char const* frozen_index_t::plan(uint32_t k, uint32_t visited_cap_override, laun
     /* scratch per warp. `scale` (1, 8, 64, ...) grows it for the retry of overflowed queries. */
     uint64_t const scale = visited_cap_override ? visited_cap_override : 1;
     uint64_t const enough = (uint64_t)2 * ((uint64_t)d.n + d.m0 + 1); /* a hash table this large can never overflow */
-    static int const forced = [] { /* test hook: USEARCH_B200_VISITED=hash|bitmap */
+    static int const forced = [] { /* test hook: USEARCH_B200_VISITED=hash|bitmap|bitmap_log */
         char const* v = std::getenv("USEARCH_B200_VISITED");
-        return !v ? 0 : (std::strcmp(v, "hash") == 0 ? 1 : (std::strcmp(v, "bitmap") == 0 ? 2 : 0));
+        return !v ? 0 : (std::strcmp(v, "hash") == 0 ? 1 : (std::strcmp(v, "bitmap") == 0 ? 2 : (std::strcmp(v, "bitmap_log") == 0 ? 3 : 0)));
     }();
     static uint64_t const shrink = [] { /* test hook: start with undersized scratch to exercise the retry path */
         char const* v = std::getenv("USEARCH_B200_SCRATCH_SHRINK");
         return v && std::atoi(v) > 0 ? (uint64_t)std::atoi(v) : (uint64_t)1;
     }();
-    if (forced == 2 || (forced == 0 && (uint64_t)d.n <= BITMAP_MAX_SLOTS)) {
+    uint64_t const bitmap_words = round_up((d.n + 31) / 32, 4);
+    uint64_t const max_warps_guess = (uint64_t)sm_count * 32;
+    bool const bitmaps_fit = bitmap_words * 4 * std::min<uint64_t>(max_warps_guess, (uint64_t)sm_count * pl.warps_per_sm_target) <= BITMAP_SCRATCH_BUDGET;
+    if (forced == 2 || forced == 3 || (forced == 0 && bitmaps_fit)) {
         /* BITMAP visits: one bit per slot, exact, never overflows */
-        pl.visited_bitmap_words = round_up((d.n + 31) / 32, 4);
+        pl.visited_bitmap_words = (uint32_t)bitmap_words;
         pl.visited_cap = 0;
+        pl.visit_log_cap = (forced == 3 || (forced == 0 && (uint64_t)d.n > BITMAP_WIPE_MAX_SLOTS))
+                               ? (uint32_t)std::max<uint64_t>(32768 / shrink, 64) : 0u;
         uint64_t spill = std::max<uint64_t>(1024, (uint64_t)8 * ef) * scale / shrink;
         spill = std::max<uint64_t>(spill, 16);
         pl.heap_spill_cap = (uint32_t)std::min<uint64_t>(spill, (uint64_t)d.n + 1);
         pl.maxed = pl.heap_spill_cap >= d.n;
     } else {
         pl.visited_bitmap_words = 0;
+        pl.visit_log_cap = 0;
         uint64_t want = std::max<uint64_t>((uint64_t)2 * ef * d.m0 * scale, 2048) / shrink;
         pl.visited_cap = std::max<uint32_t>(ceil2(std::min<uint64_t>(want, enough)), 64);
         /* pushes <= visited entries <= cap/2, so this spill can not overflow before `visits` does */
@@ -491,7 +498,22 @@ char const* frozen_index_t::search_device(void const* d_queries, size_t nq, size
     if (char const* e = work_counter.reserve(2)) return e;
     if (char const* e = status.reserve(nq)) return e;
     if (char const* e = h_status.reserve(nq)) return e;
-    if (char const* e = visited.reserve(warps * pl.visited_words_per_warp())) return e;
+    auto reserve_visits = [&](launch_plan_t const& p, size_t nwarps) -> char const* {
+        size_t const words = nwarps * p.visited_words_per_warp();
+        bool const grown = words > visited.capacity;
+        if (char const* e = visited.reserve(words)) return e;
+        if (grown) visited_zeroed_words = 0;
+        if (p.visit_log_cap) { /* logged bitmaps rely on an all-zero slab between queries */
+            if (char const* e = visit_log.reserve(nwarps * p.visit_log_cap)) return e;
+            if (visited_zeroed_words < words) {
+                if (cudaMemsetAsync(visited.ptr, 0, words * 4, s) != cudaSuccess) return "CUDA failure: memset";
+                visited_zeroed_words = words;
+            }
+        } else
+            visited_zeroed_words = 0; /* wiped per query with other contents in between */
+        return nullptr;
+    };
+    if (char const* e = reserve_visits(pl, warps)) return e;
     if (char const* e = heap_spill.reserve(warps * pl.heap_spill_cap)) return e;
 
     search_args_t a;
@@ -511,6 +533,8 @@ char const* frozen_index_t::search_device(void const* d_queries, size_t nq, size
     a.visited = visited.ptr;
     a.visited_cap = pl.visited_cap;
     a.visited_bitmap_words = pl.visited_bitmap_words;
+    a.visit_log = pl.visit_log_cap ? visit_log.ptr : nullptr;
+    a.visit_log_cap = pl.visit_log_cap;
     a.heap_spill = heap_spill.ptr;
     a.heap_spill_cap = pl.heap_spill_cap;
     a.heap_smem_cap = pl.heap_smem_cap;
@@ -555,7 +579,7 @@ char const* frozen_index_t::search_device(void const* d_queries, size_t nq, size
         int rblocks = (int)std::min<size_t>({(size_t)rp.blocks, (failed.size() + wpb - 1) / wpb, max_warps / wpb});
         rblocks = std::max(rblocks, 1);
         size_t rwarps = (size_t)rblocks * wpb;
-        if (char const* e = visited.reserve(rwarps * rp.visited_words_per_warp())) return e;
+        if (char const* e = reserve_visits(rp, rwarps)) return e;
         if (char const* e = heap_spill.reserve(rwarps * rp.heap_spill_cap)) return e;
         if (char const* e = retry_list.reserve(failed.size())) return e;
         CU(cudaMemcpyAsync(retry_list.ptr, failed.data(), failed.size() * 4, cudaMemcpyHostToDevice, s));
@@ -568,6 +592,8 @@ char const* frozen_index_t::search_device(void const* d_queries, size_t nq, size
         r.visited = visited.ptr;
         r.visited_cap = rp.visited_cap;
         r.visited_bitmap_words = rp.visited_bitmap_words;
+        r.visit_log = rp.visit_log_cap ? visit_log.ptr : nullptr;
+        r.visit_log_cap = rp.visit_log_cap;
         r.heap_spill = heap_spill.ptr;
         r.heap_spill_cap = rp.heap_spill_cap;
         CU(cudaMemsetAsync(work_counter.ptr, 0, 8, s));

@@ -30,12 +30,14 @@ cudaError_t search_compute_norms(device_index_t const& ix, float* norms, cudaStr
 cudaError_t search_build_allow_bits(device_index_t const& ix, uint64_t const* allowed_sorted, uint32_t m, uint32_t* bits,
                                     cudaStream_t stream);
 
-/* indexes up to this many slots track `visits` as a per-warp bitmap (512 KB at the limit) */
-constexpr uint64_t BITMAP_MAX_SLOTS = 1ull << 22;
+/* `visits` is a per-warp bitmap whenever all the bitmaps fit this budget (else an open-addressing table);
+ * bitmaps above BITMAP_WIPE_MAX_SLOTS are cleaned through a log of the bits each query set */
+constexpr uint64_t BITMAP_SCRATCH_BUDGET = 12ull << 30;
+constexpr uint64_t BITMAP_WIPE_MAX_SLOTS = 1ull << 20;
 
 struct launch_plan_t {
     uint32_t ef = 0;
-    uint32_t visited_cap = 0, visited_bitmap_words = 0, heap_spill_cap = 0, heap_smem_cap = 0;
+    uint32_t visited_cap = 0, visited_bitmap_words = 0, visit_log_cap = 0, heap_spill_cap = 0, heap_smem_cap = 0;
     bool maxed = false; /* growing the scratch any further cannot help */
     size_t visited_words_per_warp() const { return visited_bitmap_words ? visited_bitmap_words : visited_cap; }
     uint32_t smem_per_warp = 0, off_top_d = 0, off_top_s = 0, off_cand_s = 0, off_cand_d = 0, off_heap = 0;
@@ -113,7 +115,8 @@ struct frozen_index_t {
     std::mutex mutex;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
-    device_buffer_t<uint32_t> visited, work_counter, status, counts, computed, cycles, retry_list;
+    device_buffer_t<uint32_t> visited, visit_log, work_counter, status, counts, computed, cycles, retry_list;
+    size_t visited_zeroed_words = 0; /* the first this-many words of `visited` are known to be zero (logged bitmaps) */
     device_buffer_t<cand_t> heap_spill;
     device_buffer_t<uint8_t> queries;
     device_buffer_t<uint64_t> allowed_keys; /* filtered search: sorted allowed keys and the bitmap built from them */

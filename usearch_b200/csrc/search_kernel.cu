@@ -470,6 +470,8 @@ __device__ __forceinline__ void search_one(device_index_t const& ix, search_args
                                            heap_t const& heap, uint32_t* visited, int lane) {
     uint32_t const k = a.k, ef = a.ef;
     uint32_t top_size = 0, heap_size = 0, computed = 0, cycles = 0, status = STATUS_OK;
+    uint32_t visited_total = 0;
+    bool log_overflow_out = false;
     bool const prof = a.phase_cycles != nullptr;
     uint32_t pc0 = 0, pc1 = 0, pc2 = 0, pc4 = 0, pc5 = 0, n_push = 0, max_heap = 0;
     long long tp = prof ? clock64() : 0;
@@ -505,7 +507,10 @@ __device__ __forceinline__ void search_one(device_index_t const& ix, search_args
         }
         /* visits.clear() */
         bool const bitmap = a.visited_bitmap_words != 0;
-        {
+        bool const logged = bitmap && a.visit_log != nullptr; /* the bitmap is already all-zero */
+        uint32_t* const vlog = logged ? a.visit_log + (size_t)blockIdx.x * a.visit_log_cap : nullptr;
+        bool log_overflow = false;
+        if (!logged) {
             uint32_t const fill = bitmap ? 0u : EMPTY_SLOT;
             uint4 const word = make_uint4(fill, fill, fill, fill);
             uint4* v4 = reinterpret_cast<uint4*>(visited);
@@ -582,6 +587,7 @@ __device__ __forceinline__ void search_one(device_index_t const& ix, search_args
             heap.set_root(cand_t{radius, closest});
             if (bitmap) atomicOr(&visited[closest >> 5], 1u << (closest & 31));
             else atomicCAS(&visited[hash_slot(closest) & vmask], EMPTY_SLOT, closest);
+            if (logged) vlog[0] = closest;
         }
         heap_size = 1;
         visited_count = 1;
@@ -648,6 +654,13 @@ __device__ __forceinline__ void search_one(device_index_t const& ix, search_args
                 ncand = __popc(bal0);
                 if (f1) cand_s[ncand + __popc(bal1 & lt)] = s1;
                 ncand += __popc(bal1);
+                if (logged) { /* remember which bits this query set */
+                    if (visited_count + ix.m0 > a.visit_log_cap) log_overflow = true;
+                    if (!log_overflow) {
+                        if (f0) vlog[visited_count + __popc(bal0 & lt)] = s0;
+                        if (f1) vlog[visited_count + __popc(bal0) + __popc(bal1 & lt)] = s1;
+                    }
+                }
                 for (uint32_t b = 64; b < ix.m0; b += 32) {
                     uint32_t i = b + lane;
                     uint32_t s = i < ix.m0 ? __ldg(row + i) : EMPTY_SLOT;
@@ -655,6 +668,7 @@ __device__ __forceinline__ void search_one(device_index_t const& ix, search_args
                     bool f = s != EMPTY_SLOT && !((o >> (s & 31)) & 1u);
                     uint32_t bal = __ballot_sync(0xffffffffu, f);
                     if (f) cand_s[ncand + __popc(bal & lt)] = s;
+                    if (logged && !log_overflow && f) vlog[visited_count + ncand + __popc(bal & lt)] = s;
                     ncand += __popc(bal);
                 }
             } else {
@@ -721,6 +735,22 @@ __device__ __forceinline__ void search_one(device_index_t const& ix, search_args
             PHASE(pc5)
             if (status != STATUS_OK) break;
         }
+        visited_total = visited_count;
+        log_overflow_out = log_overflow;
+    }
+
+    /* leave the logged bitmap all-zero for the next query of this warp */
+    if (ix.n != 0 && k != 0 && a.visited_bitmap_words != 0 && a.visit_log != nullptr) {
+        __syncwarp();
+        if (!log_overflow_out) {
+            uint32_t const* vlog = a.visit_log + (size_t)blockIdx.x * a.visit_log_cap;
+            for (uint32_t i = lane; i < visited_total; i += 32) visited[vlog[i] >> 5] = 0u;
+        } else {
+            uint4 const zero = make_uint4(0u, 0u, 0u, 0u);
+            uint4* v4 = reinterpret_cast<uint4*>(visited);
+            for (uint32_t j = lane; j < a.visited_bitmap_words / 4; j += 32) v4[j] = zero;
+        }
+        __threadfence_block();
     }
 
     /* ---- dump_to (index.hpp:2707-2722) ---- */
