@@ -149,7 +149,7 @@ void usearch_exact_search(void const* dataset, size_t dataset_size, size_t datas
                           size_t queries_size, size_t queries_stride, usearch_scalar_kind_t scalar_kind, size_t dimensions,
                           usearch_metric_kind_t metric_kind, size_t count, size_t threads, usearch_key_t* keys,
                           size_t keys_stride, usearch_distance_t* distances, size_t distances_stride,
-                          usearch_error_t* error); /* usearch.h:467 */
+                          usearch_error_t* error); /* usearch.h:467; runs on the GPU, `threads` ignored, count <= 256 */
 void usearch_clear(usearch_index_t index, usearch_error_t* error); /* usearch.h:481 */
 
 /* ---- additive, device-resident variants ---------------------------------------------------- */
@@ -182,6 +182,14 @@ size_t usearch_b200_filtered_search_many(usearch_index_t index, void const* quer
                                          usearch_key_t const* allowed_keys, size_t allowed_count, usearch_key_t* keys,
                                          usearch_distance_t* distances, size_t* counts, uint64_t* computed_distances,
                                          uint64_t* visited_members, usearch_error_t* error);
+
+/* `search(exact = true)` of the reference's C++ / Python surface (index.hpp:3047-3051, search_exact_ :4251-4268) for a
+ * batch: brute force over every non-removed member of the frozen index, ties resolved exactly like the reference's
+ * sequence of sorted inserts (equal distances: larger slot first). count <= 256. */
+size_t usearch_b200_exact_search_many(usearch_index_t index, void const* queries, size_t queries_count,
+                                      size_t queries_stride, usearch_scalar_kind_t query_kind, size_t count,
+                                      usearch_key_t* keys, usearch_distance_t* distances, size_t* counts,
+                                      usearch_error_t* error);
 
 /* Phase introspection of the search kernel: enable != 0 turns on (and zeroes) sixteen device-side
  * counters summed over all queries since; `counters16` (may be NULL) first receives the current values:

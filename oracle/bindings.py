@@ -80,6 +80,9 @@ def ref_lib(flavour: str = "parity") -> C.CDLL | None:
                                     _u64p, _f32p, _u64p, _u64p, _u64p, C.POINTER(C.c_char_p)]
     lib.ref_filtered_search_many_f32.argtypes = [C.c_void_p, _f32p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, _u64p,
                                                  C.c_size_t, _u64p, _f32p, _u64p, _u64p, _u64p, C.POINTER(C.c_char_p)]
+    lib.ref_exact_search.restype = C.c_int
+    lib.ref_exact_search.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int,
+                                     C.c_size_t, C.c_size_t, C.c_int, _u64p, _f32p]
     lib.ref_cast_from_f32.restype = C.c_size_t
     lib.ref_cast_from_f32.argtypes = [C.c_int, _f32p, C.c_size_t, C.c_void_p]
     lib.ref_hardware_threads.restype = C.c_size_t
@@ -202,6 +205,23 @@ def _ref_filtered_search(self, queries: np.ndarray, k: int, allowed_keys: np.nda
 
 
 RefIndex.filtered_search = _ref_filtered_search
+
+def ref_exact_search(dataset: np.ndarray, queries: np.ndarray, k: int, *, metric: str, scalar: str, dims: int,
+                     pinned: bool = True, flavour: str = "parity"):
+    """exact_search_t of the reference over raw matrices (rows in `scalar` kind); keys are dataset row numbers."""
+    lib = ref_lib(flavour)
+    dataset = np.ascontiguousarray(dataset)
+    queries = np.ascontiguousarray(queries)
+    nq = queries.shape[0]
+    keys = np.zeros((nq, k), dtype=np.uint64)
+    dist = np.zeros((nq, k), dtype=np.float32)
+    rc = lib.ref_exact_search(dataset.ctypes.data_as(C.c_void_p), dataset.shape[0], dataset.strides[0],
+                              queries.ctypes.data_as(C.c_void_p), nq, queries.strides[0], METRIC[metric],
+                              SCALAR[scalar], dims, k, int(pinned), _ptr(keys, _u64p), _ptr(dist, _f32p))
+    if rc:
+        raise RuntimeError(f"ref_exact_search failed: {rc}")
+    return keys, dist
+
 
 _port_lib: C.CDLL | None = None
 

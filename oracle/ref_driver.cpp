@@ -192,6 +192,35 @@ int ref_pin_metric(void* h, int mode) {
     return 0;
 }
 
+/* exact_search_t (index_plugins.hpp:2071-2164) as usearch_exact_search (c/lib.cpp:468-501) drives it, single-threaded.
+ * pinned != 0 swaps the metric for the portable restatement. Outputs are dense [nq x wanted]. Returns 0 on success. */
+int ref_exact_search(void const* dataset, std::size_t n, std::size_t dataset_stride, void const* queries, std::size_t nq,
+                     std::size_t queries_stride, int metric_char, int scalar_char, std::size_t dimensions, std::size_t wanted,
+                     int pinned, std::uint64_t* keys, float* distances) {
+    metric_kind_t m = static_cast<metric_kind_t>(metric_char);
+    scalar_kind_t s = static_cast<scalar_kind_t>(scalar_char);
+    metric_punned_t metric = metric_punned_t::builtin(dimensions, m, s);
+    if (metric.missing()) return -1;
+    if (pinned) {
+#if defined(__FAST_MATH__)
+        return -2;
+#endif
+        std::uintptr_t fn = pinned_for(m, s);
+        if (!fn) return -1;
+        metric = metric_punned_t::stateless(dimensions, fn, metric_punned_signature_t::array_array_size_k, m, s);
+    }
+    exact_search_t search;
+    exact_search_results_t result = search(static_cast<byte_t const*>(dataset), n, dataset_stride,
+                                           static_cast<byte_t const*>(queries), nq, queries_stride, wanted, metric);
+    if (!result) return -3;
+    for (std::size_t q = 0; q != nq; ++q) {
+        auto row = result.at(q);
+        for (std::size_t i = 0; i != wanted; ++i)
+            keys[q * wanted + i] = row[i].offset, distances[q * wanted + i] = row[i].distance;
+    }
+    return 0;
+}
+
 /* One distance through whatever metric is currently installed (a, b in the index's scalar kind). */
 float ref_distance(void* h, void const* a, void const* b) {
     auto* r = static_cast<ref_index_t*>(h);

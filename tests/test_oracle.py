@@ -137,3 +137,18 @@ def test_v2format_roundtrip():
     g = np.load(FIXTURES[0])
     graph = v2format.loads(g["blob"])
     assert np.array_equal(v2format.dumps(graph), g["blob"])
+
+
+@pytest.mark.skipif(not common.have_reference(), reason="oracle/_ref not built")
+def test_exact_search_oracles_agree():
+    """The two brute-force oracles (exact_search_t over raw matrices, index search(exact=True)) give the same distance
+    bits for a symmetric metric, and the port's exact path matches the reference's bit for bit."""
+    base, q = common.make_collection(1500, 48, "f32", 32, iid=True)
+    ref, blob = common.build_reference_blob(base, "l2sq", "f32", 48, 8, expansion_add=16, threads=4)
+    ref.pin_metric(True)
+    want = ref.search(q, 10, threads=2, exact=True)
+    port = bindings.PortIndex(blob, 64).search(q, 10, threads=2, exact=True)
+    common.assert_same_results(want[:3], port[:3], "port exact vs reference exact")
+    fk, fd = bindings.ref_exact_search(base, q, 10, metric="l2sq", scalar="f32", dims=48, pinned=True)
+    assert np.array_equal(fd.view(np.uint32), want[1].view(np.uint32))
+    assert np.array_equal(fk, want[0])  # iid floats: no equal distances

@@ -338,11 +338,32 @@ usearch_distance_t usearch_distance(void const*, void const*, usearch_scalar_kin
     set_error(error, "Scalar distances are not offloaded: call the host library");
     return 0;
 }
-void usearch_exact_search(void const*, size_t, size_t, void const*, size_t, size_t, usearch_scalar_kind_t, size_t,
-                          usearch_metric_kind_t, size_t, size_t, usearch_key_t*, size_t, usearch_distance_t*, size_t,
-                          usearch_error_t* error) {
-    set_error(error, "Exact search is not offloaded yet: call the host library");
+void usearch_exact_search(void const* dataset, size_t dataset_size, size_t dataset_stride, void const* queries, size_t queries_size,
+                          size_t queries_stride, usearch_scalar_kind_t scalar_kind, size_t dimensions, usearch_metric_kind_t metric_kind,
+                          size_t count, size_t /*threads*/, usearch_key_t* keys, size_t keys_stride, usearch_distance_t* distances,
+                          size_t distances_stride, usearch_error_t* error) {
+    uint32_t const m = metric_to_char(metric_kind), s = scalar_to_char(scalar_kind);
+    if (!m || !s) return set_error(error, "Unknown metric kind!");
+    set_error(error, exact_search_free(dataset, dataset_size, dataset_stride, queries, queries_size, queries_stride, s, dimensions, m, count,
+                                       keys, keys_stride, distances, distances_stride));
 }
+
+size_t usearch_b200_exact_search_many(usearch_index_t index, void const* queries, size_t queries_count, size_t queries_stride,
+                                      usearch_scalar_kind_t query_kind, size_t count, usearch_key_t* keys, usearch_distance_t* distances,
+                                      size_t* counts, usearch_error_t* error) {
+    frozen_index_t* ix = as_index(index);
+    uint32_t qs = scalar_to_char(query_kind);
+    if (!qs) { set_error(error, "Unknown scalar kind!"); return 0; }
+    if (char const* e = ix->exact_host(queries, queries_count, queries_stride, qs, count, keys, distances, counts)) {
+        set_error(error, e);
+        return 0;
+    }
+    size_t total = 0;
+    if (counts)
+        for (size_t i = 0; i < queries_count; ++i) total += counts[i];
+    return total;
+}
+
 void usearch_clear(usearch_index_t index, usearch_error_t*) {
     frozen_index_t* ix = as_index(index);
     std::lock_guard<std::mutex> lock(ix->mutex);

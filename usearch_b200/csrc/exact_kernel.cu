@@ -1,0 +1,296 @@
+/*
+ *  exact_kernel.cu — brute-force ("exact") many-to-many search on the GPU.
+ *
+ *  Two reference entry points end here:
+ *    index_gt::search(exact = true) -> search_exact_      index.hpp:4251-4268
+ *        every non-deleted slot in slot order, `top.insert(candidate, count)`;
+ *    exact_search_t / usearch_exact_search                 index_plugins.hpp:2071-2164, c/lib.cpp:468-501
+ *        distance matrix, then std::partial_sort per query; the metric is called as metric(dataset, query).
+ *  Both are "the k smallest distances"; they differ in tie order. A sequence of sorted_buffer_gt::insert calls in
+ *  ascending slot order converges to the k smallest under the TOTAL order (distance ascending, slot descending),
+ *  which is what `top_insert_reg_keyed` maintains — in any insertion order, so the dataset can be cut into
+ *  segments that are scanned by different CTAs and merged afterwards. std::partial_sort leaves ties unspecified;
+ *  the same rule is used there (distances and, where no two distances are equal, labels match the reference).
+ *
+ *  Distances are computed by the very metric structs of the search kernel (metrics.cuh): one (query, vector)
+ *  pair yields the same bits in both kernels.
+ *
+ *  Work layout: a CTA owns W queries (one warp each, query in shared memory) and one segment of the dataset;
+ *  thread 0 streams tiles of VPP vectors into a double-buffered shared-memory stage with TMA bulk copies and
+ *  all W warps reduce every tile against their own query, so each vector is fetched once per W queries.
+ */
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <type_traits>
+
+#include "device_index.h"
+#include "frozen_index.h"
+#include "metrics.cuh"
+#include "warp_primitives.cuh"
+
+namespace usearch_b200 {
+
+constexpr int EXACT_WARPS = 8;
+
+struct exact_args_t {
+    uint8_t const* queries = nullptr; /* rows padded to vec_stride, index scalar kind */
+    uint64_t query_stride = 0;
+    uint32_t nq = 0, k = 0;
+    uint32_t segments = 1, segment_len = 0; /* dataset cut into `segments` runs of `segment_len` slots (multiple of VPP) */
+    float* part_d = nullptr;                /* [nq x segments x k] */
+    uint32_t* part_s = nullptr;
+    uint32_t* part_n = nullptr;             /* [nq x segments] */
+    uint64_t* out_keys = nullptr;           /* [nq x k] */
+    float* out_dists = nullptr;
+    uint32_t* out_counts = nullptr;
+    uint32_t stage_stride = 0, off_bars = 0, off_stage = 0;
+    uint32_t slots_as_keys = 0;             /* 1: report the slot number as the key (free-function mode) */
+};
+
+template <class M, class = void> struct has_finish_sw : std::false_type {};
+template <class M> struct has_finish_sw<M, decltype((void)&M::finish_sw, void())> : std::true_type {};
+
+template <class M, bool SWAP>
+__device__ __forceinline__ float finish_ordered(typename M::acc_t const& acc, typename M::qconst_t qc) {
+    if constexpr (SWAP && has_finish_sw<M>::value) return M::finish_sw(acc, qc);
+    else return M::finish(acc, qc);
+}
+
+template <class M, bool SWAP>
+__global__ void __launch_bounds__(EXACT_WARPS * 32) exact_scan_kernel(__grid_constant__ device_index_t const ix,
+                                                                      __grid_constant__ exact_args_t const a) {
+    constexpr int LPV = M::LPV, VPP = 32 / LPV;
+    extern __shared__ __align__(128) uint8_t smem[];
+    int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane / LPV, sub = lane % LPV;
+    uint32_t const chunks = ix.chunks16, bytes = (uint32_t)ix.vec_stride;
+    uint4* const q4 = reinterpret_cast<uint4*>(smem + (size_t)warp * bytes);
+    uint32_t const bars = smem_u32(smem + a.off_bars), stage_addr = smem_u32(smem + a.off_stage);
+    uint32_t const qi = blockIdx.x * EXACT_WARPS + warp;
+    bool const has_query = qi < a.nq;
+    uint32_t const seg_lo = blockIdx.y * a.segment_len, seg_hi = min(ix.n, seg_lo + a.segment_len);
+    uint32_t const ntiles = seg_hi > seg_lo ? (seg_hi - seg_lo + VPP - 1) / VPP : 0;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bars, 1);
+        mbar_init(bars + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (has_query) {
+        uint4 const* src = reinterpret_cast<uint4 const*>(a.queries + (size_t)qi * a.query_stride);
+        for (uint32_t j = lane; j < chunks; j += 32) q4[j] = src[j];
+    }
+    __syncthreads();
+    typename M::qconst_t qc = M::prepare(q4, chunks, lane);
+
+    auto issue = [&](uint32_t t) { /* thread 0 only */
+        uint32_t const base = seg_lo + t * VPP, cnt = min((uint32_t)VPP, seg_hi - base), set = t & 1u;
+        mbar_expect_tx(bars + 8u * set, cnt * bytes);
+        for (uint32_t i = 0; i < cnt; ++i)
+            bulk_copy_g2s(stage_addr + (set * VPP + i) * a.stage_stride, ix.vectors + (size_t)(base + i) * ix.vec_stride, bytes,
+                          bars + 8u * set);
+    };
+    if (threadIdx.x == 0 && ntiles) issue(0);
+
+    float td[TOP_E];
+    uint32_t ts[TOP_E];
+#pragma unroll
+    for (int j = 0; j < TOP_E; ++j) { td[j] = 0.f; ts[j] = 0u; }
+    uint32_t top_size = 0, phase = 0;
+    float worst = 0.f;
+
+    for (uint32_t t = 0; t < ntiles; ++t) {
+        uint32_t const set = t & 1u, base = seg_lo + t * VPP, cnt = min((uint32_t)VPP, seg_hi - base);
+        if (threadIdx.x == 0 && t + 1 < ntiles) issue(t + 1); /* the other set was released by the barrier below */
+        mbar_wait(bars + 8u * set, (phase >> set) & 1u);
+        phase ^= 1u << set;
+        uint32_t const slot = base + (uint32_t)g;
+        bool const act = has_query && (uint32_t)g < cnt;
+        typename M::acc_t acc;
+        M::init(acc);
+        if (act) {
+            uint4 const* buf = reinterpret_cast<uint4 const*>(smem + a.off_stage + (size_t)(set * VPP + g) * a.stage_stride);
+            uint32_t j = sub;
+            for (; j + 3 * LPV < chunks; j += 4 * LPV) {
+                uint4 b0 = buf[j], b1 = buf[j + LPV], b2 = buf[j + 2 * LPV], b3 = buf[j + 3 * LPV];
+                uint4 q0 = q4[j], q1 = q4[j + LPV], q2 = q4[j + 2 * LPV], q3 = q4[j + 3 * LPV];
+                M::step(acc, b0, q0);
+                M::step(acc, b1, q1);
+                M::step(acc, b2, q2);
+                M::step(acc, b3, q3);
+            }
+            for (; j < chunks; j += LPV) M::step(acc, buf[j], q4[j]);
+        }
+        float d = finish_ordered<M, SWAP>(acc, qc);
+        if constexpr (M::NORMS) {
+            float const b2 = act ? __ldg(ix.norms + slot) : 0.f;
+            d = SWAP ? M::finalize_sw(d, qc, b2) : M::finalize(d, qc, b2);
+        }
+        bool keep = act && sub == 0;
+        if (keep && ix.deleted_bits) keep = !((ix.deleted_bits[slot >> 5] >> (slot & 31)) & 1u);
+        /* candidates that can still enter: everything while the list is short, then d <= worst (an equal distance
+         * with a larger slot number goes in front of the old one) */
+        uint32_t todo = __ballot_sync(0xffffffffu, keep && (top_size < a.k || !(d > worst)));
+        while (todo) {
+            int const src_lane = __ffs(todo) - 1;
+            todo &= todo - 1;
+            float const cd = __shfl_sync(0xffffffffu, d, src_lane);
+            uint32_t const cs = base + (uint32_t)(src_lane / LPV);
+            if (top_size < a.k || !(cd > worst)) {
+                top_insert_reg_keyed(td, ts, top_size, a.k, cd, cs, lane);
+                worst = top_back_reg(td, top_size);
+            }
+        }
+        __syncthreads(); /* every warp is done with this set before thread 0 refills it */
+    }
+
+    if (has_query) { /* partial result of this (query, segment) */
+        size_t const row = ((size_t)qi * a.segments + blockIdx.y) * a.k;
+#pragma unroll
+        for (int j = 0; j < TOP_E; ++j) {
+            uint32_t const i = (uint32_t)lane * TOP_E + (uint32_t)j;
+            if (i < top_size) { a.part_d[row + i] = td[j]; a.part_s[row + i] = ts[j]; }
+        }
+        if (lane == 0) a.part_n[(size_t)qi * a.segments + blockIdx.y] = top_size;
+    }
+}
+
+/* one warp per query: merge the per-segment lists under (distance asc, slot desc), map slots to keys, pad */
+__global__ void exact_merge_kernel(device_index_t ix, exact_args_t a) {
+    uint32_t const qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int const lane = threadIdx.x & 31;
+    if (qi >= a.nq) return;
+    float td[TOP_E];
+    uint32_t ts[TOP_E];
+#pragma unroll
+    for (int j = 0; j < TOP_E; ++j) { td[j] = 0.f; ts[j] = 0u; }
+    uint32_t top_size = 0;
+    for (uint32_t seg = 0; seg < a.segments; ++seg) {
+        uint32_t const n = a.part_n[(size_t)qi * a.segments + seg];
+        size_t const row = ((size_t)qi * a.segments + seg) * a.k;
+        for (uint32_t i = 0; i < n; ++i) top_insert_reg_keyed(td, ts, top_size, a.k, a.part_d[row + i], a.part_s[row + i], lane);
+    }
+#pragma unroll
+    for (int j = 0; j < TOP_E; ++j) {
+        uint32_t const i = (uint32_t)lane * TOP_E + (uint32_t)j;
+        if (i < a.k) {
+            uint64_t key = 0;
+            uint32_t bits = SNAN_BITS;
+            if (i < top_size) {
+                key = a.slots_as_keys ? (uint64_t)ts[j] : ix.keys[ts[j]];
+                bits = __float_as_uint(td[j]);
+            }
+            a.out_keys[(size_t)qi * a.k + i] = key;
+            reinterpret_cast<uint32_t*>(a.out_dists)[(size_t)qi * a.k + i] = bits;
+        }
+    }
+    if (lane == 0) a.out_counts[qi] = top_size;
+}
+
+template <class M> static cudaError_t exact_launch_t(device_index_t const& ix, exact_args_t const& a, bool swap, dim3 grid, size_t smem,
+                                                     cudaStream_t stream) {
+    if (swap) {
+        cudaError_t e = cudaFuncSetAttribute(exact_scan_kernel<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        exact_scan_kernel<M, true><<<grid, EXACT_WARPS * 32, smem, stream>>>(ix, a);
+    } else {
+        cudaError_t e = cudaFuncSetAttribute(exact_scan_kernel<M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        exact_scan_kernel<M, false><<<grid, EXACT_WARPS * 32, smem, stream>>>(ix, a);
+    }
+    return cudaGetLastError();
+}
+
+static int exact_lpv(device_index_t const& ix) {
+    if (ix.scalar == SCALAR_F16 || ix.scalar == SCALAR_BF16) return 1;
+    if (ix.scalar == SCALAR_B1) return 2;
+    return 4;
+}
+
+/*
+ *  Exact top-k of `nq` device-resident queries (index scalar kind, rows `query_stride` bytes apart, 16-byte aligned
+ *  and readable up to vec_stride) against every vector of `ix`. `swap` = call the metric as metric(stored, query).
+ *  Scratch for the per-segment partial lists is taken from `scratch` (grown on demand).
+ */
+char const* exact_search_device(device_index_t const& ix, int sm_count, void const* d_queries, size_t nq, size_t query_stride, size_t k,
+                                bool swap, bool slots_as_keys, uint64_t* d_keys, float* d_dists, uint32_t* d_counts,
+                                device_buffer_t<uint8_t>& scratch, cudaStream_t stream) {
+    if (!nq || !k) return nullptr;
+    if (k > 32 * TOP_E) return "Exact search offload supports count <= 256";
+    if (!ix.n) { /* nothing to scan: empty rows */
+        if (cudaMemsetAsync(d_counts, 0, nq * 4, stream) != cudaSuccess) return "CUDA failure: memset";
+        if (cudaMemsetAsync(d_keys, 0, nq * k * 8, stream) != cudaSuccess) return "CUDA failure: memset";
+        if (cudaMemsetAsync(d_dists, 0xFF, nq * k * 4, stream) != cudaSuccess) return "CUDA failure: memset"; /* NaN */
+        return nullptr;
+    }
+    int const lpv = exact_lpv(ix), vpp = 32 / lpv;
+    exact_args_t a;
+    a.queries = static_cast<uint8_t const*>(d_queries);
+    a.query_stride = query_stride;
+    a.nq = (uint32_t)nq;
+    a.k = (uint32_t)k;
+    a.slots_as_keys = slots_as_keys ? 1u : 0u;
+    a.stage_stride = (uint32_t)((ix.vec_stride + 127) / 128 * 128) + 16u * (uint32_t)lpv;
+    uint32_t off = EXACT_WARPS * (uint32_t)ix.vec_stride;
+    a.off_bars = off;
+    off = (off + 16 + 127) / 128 * 128;
+    a.off_stage = off;
+    size_t const smem = off + 2 * (size_t)vpp * a.stage_stride;
+    if (smem > 227 * 1024) return "Vectors too long for the exact-search stage";
+    uint32_t const groups = (uint32_t)((nq + EXACT_WARPS - 1) / EXACT_WARPS);
+    uint32_t want_ctas = (uint32_t)sm_count * 3;
+    uint32_t segments = groups >= want_ctas ? 1u : (want_ctas + groups - 1) / groups;
+    uint32_t const max_segments = std::max<uint32_t>(1, (ix.n + 4 * (uint32_t)vpp - 1) / (4 * (uint32_t)vpp));
+    segments = std::min(std::min(segments, max_segments), 65535u);
+    uint32_t seg_len = (ix.n + segments - 1) / segments;
+    seg_len = (seg_len + (uint32_t)vpp - 1) / (uint32_t)vpp * (uint32_t)vpp;
+    segments = (ix.n + seg_len - 1) / seg_len;
+    a.segments = segments;
+    a.segment_len = seg_len;
+    size_t const rows = nq * segments;
+    size_t const need = rows * k * 8 + rows * 4 + 64;
+    if (char const* e = scratch.reserve(need)) return e;
+    a.part_d = reinterpret_cast<float*>(scratch.ptr);
+    a.part_s = reinterpret_cast<uint32_t*>(scratch.ptr + rows * k * 4);
+    a.part_n = reinterpret_cast<uint32_t*>(scratch.ptr + rows * k * 8);
+    a.out_keys = d_keys;
+    a.out_dists = d_dists;
+    a.out_counts = d_counts;
+    dim3 const grid(groups, segments);
+    cudaError_t e = cudaErrorInvalidValue;
+    switch (ix.scalar) {
+    case SCALAR_F32:
+        if (ix.metric == METRIC_L2SQ) e = exact_launch_t<l2sq_f32_t>(ix, a, swap, grid, smem, stream);
+        else if (ix.metric == METRIC_IP) e = exact_launch_t<ip_f32_t>(ix, a, swap, grid, smem, stream);
+        else if (ix.metric == METRIC_COS) e = exact_launch_t<cos_f32_t>(ix, a, swap, grid, smem, stream);
+        break;
+    case SCALAR_F16:
+        if (ix.metric == METRIC_L2SQ) e = exact_launch_t<l2sq_half_t<f16_conv_t>>(ix, a, swap, grid, smem, stream);
+        else if (ix.metric == METRIC_IP) e = exact_launch_t<ip_half_t<f16_conv_t>>(ix, a, swap, grid, smem, stream);
+        else if (ix.metric == METRIC_COS) e = exact_launch_t<cos_half_t<f16_conv_t>>(ix, a, swap, grid, smem, stream);
+        break;
+    case SCALAR_BF16:
+        if (ix.metric == METRIC_L2SQ) e = exact_launch_t<l2sq_half_t<bf16_conv_t>>(ix, a, swap, grid, smem, stream);
+        else if (ix.metric == METRIC_IP) e = exact_launch_t<ip_half_t<bf16_conv_t>>(ix, a, swap, grid, smem, stream);
+        else if (ix.metric == METRIC_COS) e = exact_launch_t<cos_half_t<bf16_conv_t>>(ix, a, swap, grid, smem, stream);
+        break;
+    case SCALAR_I8:
+        if (ix.metric == METRIC_L2SQ) e = exact_launch_t<l2sq_i8_t<4>>(ix, a, swap, grid, smem, stream);
+        else if (ix.metric == METRIC_IP) e = exact_launch_t<ip_i8_t<4>>(ix, a, swap, grid, smem, stream);
+        else if (ix.metric == METRIC_COS) e = exact_launch_t<cos_i8_t<4>>(ix, a, swap, grid, smem, stream);
+        break;
+    case SCALAR_B1:
+        if (ix.metric == METRIC_HAMMING) e = exact_launch_t<hamming_b1_t<2>>(ix, a, swap, grid, smem, stream);
+        else if (ix.metric == METRIC_TANIMOTO || ix.metric == METRIC_JACCARD) e = exact_launch_t<tanimoto_b1_t<2>>(ix, a, swap, grid, smem, stream);
+        else if (ix.metric == METRIC_SORENSEN) e = exact_launch_t<sorensen_b1_t<2>>(ix, a, swap, grid, smem, stream);
+        break;
+    default: break;
+    }
+    if (e != cudaSuccess) return "CUDA failure: exact scan launch";
+    exact_merge_kernel<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, stream>>>(ix, a);
+    if (cudaGetLastError() != cudaSuccess) return "CUDA failure: exact merge launch";
+    return nullptr;
+}
+
+} // namespace usearch_b200

@@ -60,6 +60,7 @@ frozen_index_t::~frozen_index_t() {
     if (ev_begin) cudaEventDestroy(ev_begin);
     if (ev_end) cudaEventDestroy(ev_end);
     phase_cycles.release();
+    exact_scratch.release();
     visit_log.release();
     visited.release(); work_counter.release(); status.release(); counts.release(); computed.release();
     cycles.release(); retry_list.release(); heap_spill.release(); queries.release(); out_keys.release();
@@ -771,6 +772,111 @@ char const* frozen_index_t::search_host(void const* q, size_t nq, size_t stride,
         if (cycles_out) cycles_out[i] = h_cycles.ptr[i];
     }
     if (total) *total = sum;
+    return nullptr;
+}
+
+} // namespace usearch_b200
+
+
+namespace usearch_b200 {
+
+namespace {
+char const* cuda_error2(cudaError_t e) {
+    if (e == cudaSuccess) return nullptr;
+    cudaGetLastError();
+    return e == cudaErrorMemoryAllocation ? "Out of GPU memory!" : "CUDA failure in exact search";
+}
+#define CU2(call)                                               \
+    do {                                                        \
+        if (char const* err_ = cuda_error2((call))) return err_; \
+    } while (0)
+} // namespace
+
+/* index_gt::search(exact = true) (index.hpp:3047-3051 -> search_exact_ :4251-4268) for a batch of host queries */
+char const* frozen_index_t::exact_host(void const* q, size_t nq, size_t stride, uint32_t query_scalar, size_t k, uint64_t* keys,
+                                       float* dists, size_t* counts_out) {
+    if (!loaded) return "Index is empty: load a serialized index first";
+    if (nq == 0 || k == 0) return nullptr;
+    if (char const* e = ensure_context()) return e;
+    std::lock_guard<std::mutex> lock(mutex);
+    size_t const vs = d.vec_stride ? d.vec_stride : 16, bpv = d.bytes_per_vector;
+    if (char const* e = queries.reserve(nq * vs)) return e;
+    if (char const* e = out_keys.reserve(nq * k)) return e;
+    if (char const* e = out_dists.reserve(nq * k)) return e;
+    if (char const* e = counts_reserve_all(nq)) return e;
+    if (vs != bpv) CU2(cudaMemsetAsync(queries.ptr, 0, nq * vs, stream));
+    if (query_scalar == scalar) {
+        CU2(cudaMemcpy2DAsync(queries.ptr, vs, q, stride, bpv, nq, cudaMemcpyHostToDevice, stream));
+    } else {
+        if (char const* e = h_queries.reserve(nq * vs)) return e;
+        if (char const* e = cast_queries(query_scalar, scalar, dimensions, static_cast<uint8_t const*>(q), stride, nq, h_queries.ptr, vs)) return e;
+        CU2(cudaMemcpy2DAsync(queries.ptr, vs, h_queries.ptr, vs, bpv, nq, cudaMemcpyHostToDevice, stream));
+    }
+    if (char const* e = exact_search_device(d, sm_count, queries.ptr, nq, vs, k, false, false, out_keys.ptr, out_dists.ptr, counts.ptr,
+                                            exact_scratch, stream))
+        return e;
+    kernel_launches += 2;
+    CU2(cudaMemcpyAsync(keys, out_keys.ptr, nq * k * 8, cudaMemcpyDeviceToHost, stream));
+    CU2(cudaMemcpyAsync(dists, out_dists.ptr, nq * k * 4, cudaMemcpyDeviceToHost, stream));
+    CU2(cudaMemcpyAsync(h_counts.ptr, counts.ptr, nq * 4, cudaMemcpyDeviceToHost, stream));
+    CU2(cudaStreamSynchronize(stream));
+    if (counts_out)
+        for (size_t i = 0; i < nq; ++i) counts_out[i] = h_counts.ptr[i];
+    return nullptr;
+}
+
+/* usearch_exact_search (c/lib.cpp:468-501): many-to-many over raw matrices; keys are dataset row numbers */
+char const* exact_search_free(void const* dataset, size_t n, size_t dataset_stride, void const* queries_h, size_t nq, size_t queries_stride,
+                              uint32_t scalar, size_t dimensions, uint32_t metric, size_t k, uint64_t* keys, size_t keys_stride,
+                              float* distances, size_t distances_stride) {
+    if (!search_supported(metric, scalar)) return "This metric / scalar kind has no sm_100a kernel and the backend has no CPU fallback";
+    if (!nq || !k) return nullptr;
+    if (k > n) return "More neighbours requested than the dataset holds";
+    if (n >= 0xFFFFFFFFull) return "Too many entries for 32-bit slots";
+    frozen_index_t tmp;
+    if (char const* dev = std::getenv("USEARCH_B200_DEVICE")) tmp.device = std::atoi(dev);
+    if (char const* e = tmp.ensure_context()) return e;
+    size_t const bpv = (dimensions * bits_per_scalar(scalar) + 7) / 8, vs = (bpv + 15) / 16 * 16;
+    device_index_t ix;
+    ix.n = (uint32_t)n;
+    ix.dims = (uint32_t)dimensions;
+    ix.bytes_per_vector = (uint32_t)bpv;
+    ix.vec_stride = vs;
+    ix.chunks16 = (uint32_t)(vs / 16);
+    ix.metric = metric;
+    ix.scalar = scalar;
+    device_buffer_t<uint8_t> d_vectors, d_queries, scratch;
+    device_buffer_t<float> d_norms, d_dists;
+    device_buffer_t<uint64_t> d_keys;
+    device_buffer_t<uint32_t> d_counts;
+    struct release_all_t {
+        device_buffer_t<uint8_t>&a, &b, &c; device_buffer_t<float>&d, &e; device_buffer_t<uint64_t>& f; device_buffer_t<uint32_t>& g;
+        ~release_all_t() { a.release(); b.release(); c.release(); d.release(); e.release(); f.release(); g.release(); }
+    } release_all{d_vectors, d_queries, scratch, d_norms, d_dists, d_keys, d_counts};
+    if (char const* e = d_vectors.reserve(n * vs)) return e;
+    if (char const* e = d_queries.reserve(nq * vs)) return e;
+    if (char const* e = d_keys.reserve(nq * k)) return e;
+    if (char const* e = d_dists.reserve(nq * k)) return e;
+    if (char const* e = d_counts.reserve(nq)) return e;
+    cudaStream_t s = tmp.stream;
+    if (vs != bpv) {
+        CU2(cudaMemsetAsync(d_vectors.ptr, 0, n * vs, s));
+        CU2(cudaMemsetAsync(d_queries.ptr, 0, nq * vs, s));
+    }
+    CU2(cudaMemcpy2DAsync(d_vectors.ptr, vs, dataset, dataset_stride, bpv, n, cudaMemcpyHostToDevice, s));
+    CU2(cudaMemcpy2DAsync(d_queries.ptr, vs, queries_h, queries_stride, bpv, nq, cudaMemcpyHostToDevice, s));
+    ix.vectors = d_vectors.ptr;
+    if (search_needs_norms(metric, scalar)) {
+        if (char const* e = d_norms.reserve(n)) return e;
+        CU2(search_compute_norms(ix, d_norms.ptr, s));
+        ix.norms = d_norms.ptr;
+    }
+    if (char const* e = exact_search_device(ix, tmp.sm_count, d_queries.ptr, nq, vs, k, true, true, d_keys.ptr, d_dists.ptr, d_counts.ptr,
+                                            scratch, s))
+        return e;
+    CU2(cudaMemcpy2DAsync(keys, keys_stride, d_keys.ptr, k * 8, k * 8, nq, cudaMemcpyDeviceToHost, s));
+    CU2(cudaMemcpy2DAsync(distances, distances_stride, d_dists.ptr, k * 4, k * 4, nq, cudaMemcpyDeviceToHost, s));
+    CU2(cudaStreamSynchronize(s));
     return nullptr;
 }
 

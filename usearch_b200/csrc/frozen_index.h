@@ -148,11 +148,22 @@ struct frozen_index_t {
     char const* plan(uint32_t k, uint32_t visited_cap_override, launch_plan_t& plan) const;
     char const* search_device(void const* d_queries, size_t nq, size_t stride, size_t k, uint64_t* d_keys, float* d_dists,
                               uint32_t* d_counts, uint32_t* d_computed, uint32_t* d_cycles, cudaStream_t stream);
+    device_buffer_t<uint8_t> exact_scratch;
+    char const* exact_host(void const* queries, size_t nq, size_t stride, uint32_t query_scalar, size_t k, uint64_t* keys,
+                           float* dists, size_t* counts);
     char const* search_host(void const* queries, size_t nq, size_t stride, uint32_t query_scalar, size_t k, uint64_t* keys,
                             size_t keys_stride, float* dists, size_t dists_stride, size_t* counts, uint64_t* computed,
                             uint64_t* cycles, size_t* total, uint64_t const* allowed = nullptr, size_t allowed_count = 0,
                             bool filtered = false);
 };
+
+/* exact_kernel.cu */
+char const* exact_search_device(device_index_t const& ix, int sm_count, void const* d_queries, size_t nq, size_t query_stride, size_t k,
+                                bool swap, bool slots_as_keys, uint64_t* d_keys, float* d_dists, uint32_t* d_counts,
+                                device_buffer_t<uint8_t>& scratch, cudaStream_t stream);
+char const* exact_search_free(void const* dataset, size_t dataset_count, size_t dataset_stride, void const* queries,
+                              size_t queries_count, size_t queries_stride, uint32_t scalar, size_t dimensions, uint32_t metric,
+                              size_t count, uint64_t* keys, size_t keys_stride, float* distances, size_t distances_stride);
 
 /* host-side query casts (index_plugins.hpp:1105-1224) */
 char const* cast_queries(uint32_t from_scalar, uint32_t to_scalar, size_t dims, uint8_t const* src, size_t src_stride, size_t nq,

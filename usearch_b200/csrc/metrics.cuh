@@ -80,6 +80,7 @@ struct l2sq_f32_t {
     static constexpr int LPV = 4;
     static constexpr bool NORMS = false;
     template <class Q> static __device__ __forceinline__ float finalize(float raw, Q, float) { return raw; }
+    template <class Q> static __device__ __forceinline__ float finalize_sw(float raw, Q, float) { return raw; }
     struct acc_t { float v[4]; };
     struct qconst_t {};
     static __device__ __forceinline__ void init(acc_t& a) { a.v[0] = a.v[1] = a.v[2] = a.v[3] = 0.f; }
@@ -98,6 +99,7 @@ struct ip_f32_t {
     static constexpr int LPV = 4;
     static constexpr bool NORMS = false;
     template <class Q> static __device__ __forceinline__ float finalize(float raw, Q, float) { return raw; }
+    template <class Q> static __device__ __forceinline__ float finalize_sw(float raw, Q, float) { return raw; }
     struct acc_t { float v[4]; };
     struct qconst_t {};
     static __device__ __forceinline__ void init(acc_t& a) { a.v[0] = a.v[1] = a.v[2] = a.v[3] = 0.f; }
@@ -132,6 +134,8 @@ struct cos_f32_t {
     }
     static __device__ __forceinline__ float finish(acc_t const& a, qconst_t) { return reduce16_f32(a.ab); }
     static __device__ __forceinline__ float finalize(float ab, qconst_t qc, float b2) { return cos_normalize_f64(ab, qc.a2, b2); }
+    /* metric(stored, query) instead of metric(query, stored): exact_search_t calls it that way (index_plugins.hpp:2112) */
+    static __device__ __forceinline__ float finalize_sw(float ab, qconst_t qc, float b2) { return cos_normalize_f64(ab, b2, qc.a2); }
     /* dot(v, v) in the 16-accumulator order; every 4-lane group computes the same value */
     static __device__ __forceinline__ float self_dot(uint4 const* v4, uint32_t chunks16, int lane) {
         float v[4] = {0.f, 0.f, 0.f, 0.f};
@@ -191,6 +195,7 @@ template <class C> struct l2sq_half_t {
     static constexpr int LPV = 1;
     static constexpr bool NORMS = false;
     template <class Q> static __device__ __forceinline__ float finalize(float raw, Q, float) { return raw; }
+    template <class Q> static __device__ __forceinline__ float finalize_sw(float raw, Q, float) { return raw; }
     struct acc_t { float v[8]; };
     struct qconst_t {};
     static __device__ __forceinline__ void init(acc_t& a) {
@@ -215,6 +220,7 @@ template <class C> struct ip_half_t {
     static constexpr int LPV = 1;
     static constexpr bool NORMS = false;
     template <class Q> static __device__ __forceinline__ float finalize(float raw, Q, float) { return raw; }
+    template <class Q> static __device__ __forceinline__ float finalize_sw(float raw, Q, float) { return raw; }
     struct acc_t { float v[8]; };
     struct qconst_t {};
     static __device__ __forceinline__ void init(acc_t& a) {
@@ -254,6 +260,7 @@ template <class C> struct cos_half_t {
     }
     static __device__ __forceinline__ float finish(acc_t const& a, qconst_t) { return __double2float_rn(reduce8_f64(a.v)); }
     static __device__ __forceinline__ float finalize(float ab, qconst_t qc, float b2) { return cos_normalize_f32(ab, qc.a2, b2); }
+    static __device__ __forceinline__ float finalize_sw(float ab, qconst_t qc, float b2) { return cos_normalize_f32(ab, b2, qc.a2); }
     static __device__ __forceinline__ float self_dot(uint4 const* v4, uint32_t chunks16, int) {
         float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         for (uint32_t j = 0; j < chunks16; ++j) {
@@ -275,6 +282,7 @@ template <int LPV_> struct ip_i8_t {
     static constexpr int LPV = LPV_;
     static constexpr bool NORMS = false;
     template <class Q> static __device__ __forceinline__ float finalize(float raw, Q, float) { return raw; }
+    template <class Q> static __device__ __forceinline__ float finalize_sw(float raw, Q, float) { return raw; }
     struct acc_t { int ab; };
     struct qconst_t {};
     static __device__ __forceinline__ void init(acc_t& a) { a.ab = 0; }
@@ -295,6 +303,7 @@ template <int LPV_> struct l2sq_i8_t {
     static constexpr int LPV = LPV_;
     static constexpr bool NORMS = false;
     template <class Q> static __device__ __forceinline__ float finalize(float raw, Q, float) { return raw; }
+    template <class Q> static __device__ __forceinline__ float finalize_sw(float raw, Q, float) { return raw; }
     struct acc_t { int d2; };
     struct qconst_t {};
     static __device__ __forceinline__ void init(acc_t& a) { a.d2 = 0; }
@@ -318,6 +327,7 @@ template <int LPV_> struct cos_i8_t {
     static constexpr int LPV = LPV_;
     static constexpr bool NORMS = false;
     template <class Q> static __device__ __forceinline__ float finalize(float raw, Q, float) { return raw; }
+    template <class Q> static __device__ __forceinline__ float finalize_sw(float raw, Q, float) { return raw; }
     struct acc_t { int ab, b2; };
     struct qconst_t { int a2; };
     static __device__ __forceinline__ void init(acc_t& a) { a.ab = a.b2 = 0; }
@@ -330,6 +340,10 @@ template <int LPV_> struct cos_i8_t {
     static __device__ __forceinline__ float finish(acc_t const& a, qconst_t qc) {
         int ab = reduce_add_i32<LPV>(a.ab), b2 = reduce_add_i32<LPV>(a.b2);
         return cos_normalize_f32((float)ab, (float)qc.a2, (float)b2);
+    }
+    static __device__ __forceinline__ float finish_sw(acc_t const& a, qconst_t qc) {
+        int ab = reduce_add_i32<LPV>(a.ab), b2 = reduce_add_i32<LPV>(a.b2);
+        return cos_normalize_f32((float)ab, (float)b2, (float)qc.a2);
     }
     static __device__ __forceinline__ qconst_t prepare(uint4 const* q4, uint32_t chunks16, int lane) {
         int a2 = 0;
@@ -348,6 +362,7 @@ template <int LPV_> struct hamming_b1_t {
     static constexpr int LPV = LPV_;
     static constexpr bool NORMS = false;
     template <class Q> static __device__ __forceinline__ float finalize(float raw, Q, float) { return raw; }
+    template <class Q> static __device__ __forceinline__ float finalize_sw(float raw, Q, float) { return raw; }
     struct acc_t { int d; };
     struct qconst_t {};
     static __device__ __forceinline__ void init(acc_t& a) { a.d = 0; }
@@ -362,6 +377,7 @@ template <int LPV_> struct tanimoto_b1_t {
     static constexpr int LPV = LPV_;
     static constexpr bool NORMS = false;
     template <class Q> static __device__ __forceinline__ float finalize(float raw, Q, float) { return raw; }
+    template <class Q> static __device__ __forceinline__ float finalize_sw(float raw, Q, float) { return raw; }
     struct acc_t { int and_, or_; };
     struct qconst_t {};
     static __device__ __forceinline__ void init(acc_t& a) { a.and_ = a.or_ = 0; }
@@ -380,6 +396,7 @@ template <int LPV_> struct sorensen_b1_t {
     static constexpr int LPV = LPV_;
     static constexpr bool NORMS = false;
     template <class Q> static __device__ __forceinline__ float finalize(float raw, Q, float) { return raw; }
+    template <class Q> static __device__ __forceinline__ float finalize_sw(float raw, Q, float) { return raw; }
     struct acc_t { int and_, any_; };
     struct qconst_t {};
     static __device__ __forceinline__ void init(acc_t& a) { a.and_ = a.any_ = 0; }

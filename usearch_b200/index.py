@@ -48,7 +48,7 @@ EXPORTED_SYMBOLS = [
     "usearch_exact_search", "usearch_clear",
     # additive
     "usearch_search_many", "usearch_b200_search_many_device", "usearch_b200_search_many_stats",
-    "usearch_b200_filtered_search_many",
+    "usearch_b200_filtered_search_many", "usearch_b200_exact_search_many",
     "usearch_b200_profile_phases", "usearch_b200_device", "usearch_b200_kernel_launches", "usearch_b200_last_kernel_ms",
     "usearch_b200_bytes_per_vector", "usearch_b200_max_level",
 ]
@@ -100,6 +100,12 @@ def load_library() -> C.CDLL:
     lib.usearch_b200_filtered_search_many.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int,
                                                       C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
                                                       C.c_void_p, C.c_void_p, C.c_void_p, err]
+    lib.usearch_b200_exact_search_many.restype = C.c_size_t
+    lib.usearch_b200_exact_search_many.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_size_t,
+                                                   C.c_void_p, C.c_void_p, C.c_void_p, err]
+    lib.usearch_exact_search.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int,
+                                         C.c_size_t, C.c_int, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p,
+                                         C.c_size_t, err]
     lib.usearch_b200_profile_phases.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.usearch_b200_device.argtypes = [C.c_void_p]
     lib.usearch_b200_kernel_launches.restype = C.c_uint64
@@ -298,9 +304,7 @@ class Index:
         """1-D input → :class:`Matches`; 2-D input → :class:`BatchMatches` (index.py:191-231).
 
         `threads`, `log` and `progress` are accepted for signature compatibility with index.py:700-748 and
-        ignored (one kernel launch serves the whole batch); `exact=True` is not offloaded."""
-        if exact:
-            raise NotImplementedError("exact (brute-force) search is not offloaded: use the host library")
+        ignored (one kernel launch serves the whole batch); `exact=True` brute-forces every member on the GPU."""
         vectors = np.asarray(vectors)
         single = vectors.ndim == 1
         if single:
@@ -319,7 +323,13 @@ class Index:
         counts = np.zeros(nq, dtype=np.uint64)
         err = C.c_char_p()
         vm = cd = 0
-        if _allowed is not None:
+        if exact:
+            self._lib.usearch_b200_exact_search_many(
+                self._h, vectors.ctypes.data_as(C.c_void_p), nq, vectors.strides[0], SCALAR_KIND[kind], count,
+                keys.ctypes.data_as(C.c_void_p), distances.ctypes.data_as(C.c_void_p),
+                counts.ctypes.data_as(C.c_void_p), C.byref(err))
+            _raise(err)
+        elif _allowed is not None:
             computed = np.zeros(nq, dtype=np.uint64)
             visited = np.zeros(nq, dtype=np.uint64)
             self._lib.usearch_b200_filtered_search_many(
@@ -369,3 +379,26 @@ class Index:
                                                   counts_ptr, computed_ptr or None, visited_ptr or None,
                                                   stream or None, C.byref(err))
         _raise(err)
+
+
+def exact_search(dataset: np.ndarray, queries: np.ndarray, count: int = 10, *, metric: str = "cos",
+                 dtype: Optional[str] = None) -> BatchMatches:
+    """Brute-force many-to-many search over raw matrices: `usearch.index.search(dataset, query, count, metric,
+    exact=True)` (python/usearch/index.py) -> `usearch_exact_search` (c/lib.cpp:468-501). Keys are dataset rows."""
+    lib = load_library()
+    dataset = np.ascontiguousarray(dataset)
+    queries = np.ascontiguousarray(queries)
+    if queries.ndim == 1:
+        queries = queries[None, :]
+    kind = dtype or ("bf16" if dataset.dtype == np.uint16 else _NP_TO_SCALAR[dataset.dtype])
+    dims = dataset.shape[1] * 8 if kind == "b1" else dataset.shape[1]
+    nq = queries.shape[0]
+    keys = np.zeros((nq, count), dtype=np.uint64)
+    distances = np.zeros((nq, count), dtype=np.float32)
+    err = C.c_char_p()
+    lib.usearch_exact_search(dataset.ctypes.data_as(C.c_void_p), dataset.shape[0], dataset.strides[0],
+                             queries.ctypes.data_as(C.c_void_p), nq, queries.strides[0], SCALAR_KIND[kind], dims,
+                             METRIC_KIND[metric], count, 0, keys.ctypes.data_as(C.c_void_p), keys.strides[0],
+                             distances.ctypes.data_as(C.c_void_p), distances.strides[0], C.byref(err))
+    _raise(err)
+    return BatchMatches(keys, distances, np.full(nq, count, dtype=np.uint64))
