@@ -183,6 +183,14 @@ size_t usearch_b200_filtered_search_many(usearch_index_t index, void const* quer
                                          usearch_distance_t* distances, size_t* counts, uint64_t* computed_distances,
                                          uint64_t* visited_members, usearch_error_t* error);
 
+/* `index_dense_gt::cluster(vector, level)` (index_dense.hpp:788-793, index.hpp:3092-3125) for a batch: the closest
+ * member on graph level `level` for every query (greedy descent only). Outputs hold one entry per query;
+ * computed_distances / visited_members may be NULL. */
+void usearch_b200_cluster_many(usearch_index_t index, void const* queries, size_t queries_count, size_t queries_stride,
+                               usearch_scalar_kind_t query_kind, size_t level, usearch_key_t* keys,
+                               usearch_distance_t* distances, uint64_t* computed_distances, uint64_t* visited_members,
+                               usearch_error_t* error);
+
 /* `search(exact = true)` of the reference's C++ / Python surface (index.hpp:3047-3051, search_exact_ :4251-4268) for a
  * batch: brute force over every non-removed member of the frozen index, ties resolved exactly like the reference's
  * sequence of sorted inserts (equal distances: larger slot first). count <= 256. */

@@ -197,21 +197,48 @@ class index_dense_t {
     std::size_t max_level() const { return usearch_b200_max_level(handle_); }
     usearch_index_t native_handle() const noexcept { return handle_; }
 
-    /* index_dense.hpp:767-772 — `thread` and `exact` are accepted and ignored / rejected */
+    /* index_dense.hpp:767-772 — `thread` is accepted and ignored; `exact` scans every member (index.hpp:4251-4268) */
     template <typename scalar_at>
     search_result_t search(scalar_at const* vector, std::size_t wanted, std::size_t /*thread*/ = 0, bool exact = false) const {
         search_result_t result;
-        if (exact) return result.failed("Exact search is not offloaded yet: call the host library");
         if (!wanted) return result;
         result.keys_.resize(wanted);
         result.distances_.resize(wanted);
         std::size_t count = 0;
         std::uint64_t computed = 0, visited = 0;
         usearch_error_t error = nullptr;
+        if (exact) {
+            usearch_b200_exact_search_many(handle_, vector, 1, 0, scalar_kind<scalar_at>(), wanted, result.keys_.data(),
+                                           result.distances_.data(), &count, &error);
+            if (error) return result.failed(error);
+            result.count = count;
+            result.computed_distances = size();
+            return result;
+        }
         usearch_b200_search_many_stats(handle_, vector, 1, 0, scalar_kind<scalar_at>(), wanted, result.keys_.data(),
                                        result.distances_.data(), &count, &computed, &visited, &error);
         if (error) return result.failed(error);
         result.count = count;
+        result.computed_distances = computed;
+        result.visited_members = visited;
+        return result;
+    }
+
+    /* cluster_result_t (index.hpp:2744-2755) and index_dense_gt::cluster(vector, level) (index_dense.hpp:788-793) */
+    struct cluster_result_t {
+        error_t error{};
+        std::size_t visited_members = 0;
+        std::size_t computed_distances = 0;
+        struct match_t { struct member_t { vector_key_t key; } member; distance_t distance; } cluster{};
+        explicit operator bool() const noexcept { return !error; }
+    };
+    template <typename scalar_at> cluster_result_t cluster(scalar_at const* vector, std::size_t level, std::size_t /*thread*/ = 0) const {
+        cluster_result_t result;
+        std::uint64_t computed = 0, visited = 0;
+        usearch_error_t error = nullptr;
+        usearch_b200_cluster_many(handle_, vector, 1, 0, scalar_kind<scalar_at>(), level, &result.cluster.member.key,
+                                  &result.cluster.distance, &computed, &visited, &error);
+        result.error = error;
         result.computed_distances = computed;
         result.visited_members = visited;
         return result;

@@ -80,6 +80,8 @@ def ref_lib(flavour: str = "parity") -> C.CDLL | None:
                                     _u64p, _f32p, _u64p, _u64p, _u64p, C.POINTER(C.c_char_p)]
     lib.ref_filtered_search_many_f32.argtypes = [C.c_void_p, _f32p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, _u64p,
                                                  C.c_size_t, _u64p, _f32p, _u64p, _u64p, _u64p, C.POINTER(C.c_char_p)]
+    lib.ref_cluster_many.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, _u64p, _f32p, _u64p, _u64p,
+                                     C.POINTER(C.c_char_p)]
     lib.ref_exact_search.restype = C.c_int
     lib.ref_exact_search.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int,
                                      C.c_size_t, C.c_size_t, C.c_int, _u64p, _f32p]
@@ -206,6 +208,24 @@ def _ref_filtered_search(self, queries: np.ndarray, k: int, allowed_keys: np.nda
 
 RefIndex.filtered_search = _ref_filtered_search
 
+
+def _ref_cluster(self, queries: np.ndarray, level: int):
+    """index_dense_gt::cluster(vector, level) per row: (keys, distances, computed_distances, visited_members)."""
+    queries = np.ascontiguousarray(queries)
+    nq = queries.shape[0]
+    keys = np.zeros(nq, dtype=np.uint64)
+    dist = np.zeros(nq, dtype=np.float32)
+    computed = np.zeros(nq, dtype=np.uint64)
+    visited = np.zeros(nq, dtype=np.uint64)
+    err = C.c_char_p()
+    self.lib.ref_cluster_many(self.h, _ptr(queries), nq, queries.strides[0], level, _ptr(keys, _u64p), _ptr(dist, _f32p),
+                              _ptr(computed, _u64p), _ptr(visited, _u64p), C.byref(err))
+    _check(err)
+    return keys, dist, computed, visited
+
+
+RefIndex.cluster = _ref_cluster
+
 def ref_exact_search(dataset: np.ndarray, queries: np.ndarray, k: int, *, metric: str, scalar: str, dims: int,
                      pinned: bool = True, flavour: str = "parity"):
     """exact_search_t of the reference over raw matrices (rows in `scalar` kind); keys are dataset row numbers."""
@@ -245,6 +265,7 @@ def port_lib() -> C.CDLL:
     lib.oracle_distance.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.oracle_search_many.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int,
                                        _u64p, _f32p, _u64p, _u64p, _u64p]
+    lib.oracle_cluster_many.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, _u64p, _f32p, _u64p, _u64p]
     lib.oracle_cast_from_f32.restype = C.c_size_t
     lib.oracle_cast_from_f32.argtypes = [C.c_int, _f32p, C.c_size_t, C.c_void_p]
     _port_lib = lib
@@ -293,3 +314,14 @@ class PortIndex:
                                     int(exact), _ptr(keys, _u64p), _ptr(dist, _f32p), _ptr(counts, _u64p),
                                     _ptr(computed, _u64p), _ptr(visited, _u64p))
         return keys, dist, counts, computed, visited
+
+    def cluster(self, queries: np.ndarray, level: int):
+        queries = np.ascontiguousarray(queries)
+        nq = queries.shape[0]
+        keys = np.zeros(nq, dtype=np.uint64)
+        dist = np.zeros(nq, dtype=np.float32)
+        computed = np.zeros(nq, dtype=np.uint64)
+        visited = np.zeros(nq, dtype=np.uint64)
+        self.lib.oracle_cluster_many(self.h, _ptr(queries), nq, queries.strides[0] if nq else 0, level, _ptr(keys, _u64p),
+                                     _ptr(dist, _f32p), _ptr(computed, _u64p), _ptr(visited, _u64p))
+        return keys, dist, computed, visited

@@ -500,3 +500,22 @@ size_t oracle_cast_from_f32(int scalar_kind, float const* in, size_t d, void* ou
     default: return 0;
     }
 }
+
+/* index_gt::cluster (index.hpp:3092-3125): the descent alone, stopped above `level - 1` (level 0 behaves like level 1),
+ * then one more measurement of the winner. Single-threaded batch. */
+void oracle_cluster_many(oracle_index_t const* ix, void const* queries, size_t nq, size_t stride_bytes, size_t level,
+                         uint64_t* keys, float* distances, uint64_t* computed, uint64_t* visited) {
+    context_t c;
+    memset(&c, 0, sizeof(c));
+    for (size_t i = 0; i < nq && ix->size; ++i) {
+        void const* q = (uint8_t const*)queries + i * stride_bytes;
+        uint64_t computed0 = c.computed_distances, cycles0 = c.iteration_cycles;
+        uint32_t closest = search_for_one(ix, &c, q, (uint32_t)ix->entry_slot, (int64_t)ix->max_level,
+                                          level == 0 ? 0 : (int64_t)level - 1);
+        keys[i] = node_key(ix, closest);
+        distances[i] = measure(ix, &c, q, closest);
+        if (computed) computed[i] = c.computed_distances - computed0;
+        if (visited) visited[i] = c.iteration_cycles - cycles0;
+    }
+    context_free(&c);
+}

@@ -192,6 +192,38 @@ int ref_pin_metric(void* h, int mode) {
     return 0;
 }
 
+/* index_dense_gt::cluster(vector, level) (index_dense.hpp:788-793) for a batch, single-threaded; queries in the index's
+ * scalar kind. */
+void ref_cluster_many(void* h, void const* queries, std::size_t nq, std::size_t stride_bytes, std::size_t level,
+                      std::uint64_t* keys, float* distances, std::uint64_t* computed, std::uint64_t* visited, char const** error) {
+    *error = nullptr;
+    auto* r = static_cast<ref_index_t*>(h);
+    if (!ensure_threads(r, r->index.size(), 1)) {
+        *error = "Out of memory!";
+        return;
+    }
+    for (std::size_t i = 0; i != nq; ++i) {
+        byte_t const* q = static_cast<byte_t const*>(queries) + i * stride_bytes;
+        index_t::cluster_result_t result;
+        switch (r->index.metric().scalar_kind()) {
+        case scalar_kind_t::f32_k: result = r->index.cluster(reinterpret_cast<f32_t const*>(q), level, 0); break;
+        case scalar_kind_t::f16_k: result = r->index.cluster(reinterpret_cast<f16_t const*>(q), level, 0); break;
+        case scalar_kind_t::bf16_k: result = r->index.cluster(reinterpret_cast<bf16_t const*>(q), level, 0); break;
+        case scalar_kind_t::i8_k: result = r->index.cluster(reinterpret_cast<i8_t const*>(q), level, 0); break;
+        case scalar_kind_t::b1x8_k: result = r->index.cluster(reinterpret_cast<b1x8_t const*>(q), level, 0); break;
+        default: *error = "Unsupported scalar kind"; return;
+        }
+        if (!result) {
+            *error = "cluster failed";
+            return;
+        }
+        keys[i] = result.cluster.member.key;
+        distances[i] = result.cluster.distance;
+        computed[i] = result.computed_distances;
+        visited[i] = result.visited_members;
+    }
+}
+
 /* exact_search_t (index_plugins.hpp:2071-2164) as usearch_exact_search (c/lib.cpp:468-501) drives it, single-threaded.
  * pinned != 0 swaps the metric for the portable restatement. Outputs are dense [nq x wanted]. Returns 0 on success. */
 int ref_exact_search(void const* dataset, std::size_t n, std::size_t dataset_stride, void const* queries, std::size_t nq,

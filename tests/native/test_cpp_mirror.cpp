@@ -70,9 +70,19 @@ int main(int argc, char** argv) {
         EXPECT(std::memcmp(&batch.distances[q * k], &want_dist[q * k], k * 4) == 0);
     }
 
-    // exact=true is refused with an error value, nothing throws (index.hpp:407-461 error_t convention)
-    index_dense_t::search_result_t refused = index.search(queries.data(), k, 0, true);
-    EXPECT(!refused && refused.error.what());
+    // exact=true scans every member: never worse than the graph search, same first hit on an easy query
+    index_dense_t::search_result_t scanned = index.search(queries.data(), k, 0, true);
+    EXPECT(scanned && scanned.size() == result.size());
+    EXPECT(scanned[0].distance <= result[0].distance);
+    for (std::size_t i = 1; i < scanned.size(); ++i) EXPECT(scanned[i - 1].distance <= scanned[i].distance);
+
+    // cluster(vector, level): level beyond the top of the graph -> the entry point, at any query
+    index_dense_t::cluster_result_t top = index.cluster(queries.data(), index.max_level() + 1);
+    index_dense_t::cluster_result_t top2 = index.cluster(queries.data() + dims, index.max_level() + 1);
+    EXPECT(top && top2 && top.cluster.member.key == top2.cluster.member.key);
+    EXPECT(top.computed_distances == 2 && top.visited_members == 0);
+    index_dense_t::cluster_result_t base = index.cluster(queries.data(), 0);
+    EXPECT(base && base.cluster.distance <= top.cluster.distance);
 
     // make() from a metric, like index_dense_gt::make(metric_punned_t, config) — unsupported pairs fail by value
     index_dense_t::state_result_t fresh = index_dense_t::make(metric_punned_t::builtin(dims, usearch_metric_cos_k, usearch_scalar_f32_k));

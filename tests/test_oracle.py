@@ -152,3 +152,22 @@ def test_exact_search_oracles_agree():
     fk, fd = bindings.ref_exact_search(base, q, 10, metric="l2sq", scalar="f32", dims=48, pinned=True)
     assert np.array_equal(fd.view(np.uint32), want[1].view(np.uint32))
     assert np.array_equal(fk, want[0])  # iid floats: no equal distances
+
+
+@pytest.mark.skipif(not common.have_reference(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("metric,scalar,n,d,m", [("cos", "f32", 4000, 32, 4), ("hamming", "b1", 4000, 64, 4)])
+def test_port_cluster_matches_live_reference(metric, scalar, n, d, m):
+    """index_gt::cluster (index.hpp:3092-3125): small connectivity -> several graph levels to stop at."""
+    base, q = common.make_collection(n, d, scalar, 100)
+    ref, blob = common.build_reference_blob(base, metric, scalar, d, m, threads=4)
+    ref.pin_metric(True)
+    port = bindings.PortIndex(blob, 64)
+    assert ref.max_level >= 3
+    for level in (0, 1, 2, ref.max_level, ref.max_level + 3):
+        want = ref.cluster(q, level)
+        got = port.cluster(q, level)
+        for a, b in zip(want, got):
+            assert np.array_equal(a.view(np.uint32) if a.dtype == np.float32 else a, b.view(np.uint32) if b.dtype == np.float32 else b)
+    # level 0 and level 1 are the same stop; beyond the top level the entry point is the answer
+    assert np.array_equal(ref.cluster(q, 0)[0], ref.cluster(q, 1)[0])
+    assert len(set(ref.cluster(q, ref.max_level + 3)[0].tolist())) == 1

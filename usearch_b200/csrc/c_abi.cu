@@ -11,6 +11,7 @@
 #include <unistd.h>
 
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 #include <new>
 
@@ -346,6 +347,19 @@ void usearch_exact_search(void const* dataset, size_t dataset_size, size_t datas
     if (!m || !s) return set_error(error, "Unknown metric kind!");
     set_error(error, exact_search_free(dataset, dataset_size, dataset_stride, queries, queries_size, queries_stride, s, dimensions, m, count,
                                        keys, keys_stride, distances, distances_stride));
+}
+
+/* index_dense_gt::cluster(vector, level) (index_dense.hpp:788-793 -> cluster_ :2088-2109 -> index.hpp:3092-3125) for a
+ * batch: the greedy descent of the search kernel stopped at `level`; one (key, distance) per query. */
+void usearch_b200_cluster_many(usearch_index_t index, void const* queries, size_t queries_count, size_t queries_stride,
+                               usearch_scalar_kind_t query_kind, size_t level, usearch_key_t* keys, usearch_distance_t* distances,
+                               uint64_t* computed_distances, uint64_t* visited_members, usearch_error_t* error) {
+    frozen_index_t* ix = as_index(index);
+    uint32_t qs = scalar_to_char(query_kind);
+    if (!qs) return set_error(error, "Unknown scalar kind!");
+    if (ix->loaded && ix->size == 0) return set_error(error, "No clusters to identify");
+    set_error(error, ix->search_host(queries, queries_count, queries_stride, qs, 1, keys, 8, distances, 4, nullptr, computed_distances,
+                                     visited_members, nullptr, nullptr, 0, false, (int)std::min<size_t>(level, 0x7FFF)));
 }
 
 size_t usearch_b200_exact_search_many(usearch_index_t index, void const* queries, size_t queries_count, size_t queries_stride,

@@ -72,6 +72,7 @@ struct search_args_t {
     uint32_t nq = 0;
     uint32_t const* query_list = nullptr; /* optional indirection (retries): work item i -> query id */
     uint32_t k = 0, ef = 0;
+    int32_t cluster_end_level = -1; /* >= 0: index_gt::cluster — stop the descent above this level, report the closest member */
     /* outputs, dense [nq x k] / [nq] indexed by query id */
     uint64_t* out_keys = nullptr;
     float* out_dists = nullptr;

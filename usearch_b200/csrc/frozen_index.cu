@@ -530,6 +530,7 @@ char const* frozen_index_t::search_device(void const* d_queries, size_t nq, size
     a.out_visited = d_cycles;
     a.status = status.ptr;
     a.allow_bits = active_allow_bits;
+    a.cluster_end_level = active_cluster_end_level;
     a.work_counter = work_counter.ptr;
     a.visited = visited.ptr;
     a.visited_cap = pl.visited_cap;
@@ -702,7 +703,7 @@ char const* cast_queries(uint32_t from, uint32_t to, size_t dims, uint8_t const*
 char const* frozen_index_t::search_host(void const* q, size_t nq, size_t stride, uint32_t query_scalar, size_t k,
                                         uint64_t* keys, size_t keys_stride, float* dists, size_t dists_stride,
                                         size_t* counts, uint64_t* computed_out, uint64_t* cycles_out, size_t* total,
-                                        uint64_t const* allowed, size_t allowed_count, bool filtered) {
+                                        uint64_t const* allowed, size_t allowed_count, bool filtered, int cluster_level) {
     if (total) *total = 0;
     if (!loaded) return "Index is empty: load a serialized index first";
     if (nq == 0 || k == 0) return nullptr;
@@ -730,8 +731,10 @@ char const* frozen_index_t::search_host(void const* q, size_t nq, size_t stride,
     /* filtered search: sort the allowed keys on the host, turn them into a bitmap over slots on the device */
     struct reset_filter_t {
         frozen_index_t* self;
-        ~reset_filter_t() { self->active_allow_bits = nullptr; }
+        ~reset_filter_t() { self->active_allow_bits = nullptr; self->active_cluster_end_level = -1; }
     } reset_filter{this};
+    /* index_gt::cluster (index.hpp:3115-3116): levels max..`level`, with level 0 treated as level 1 */
+    if (cluster_level >= 0) active_cluster_end_level = cluster_level <= 0 ? 0 : cluster_level - 1;
     if (filtered && size) {
         std::vector<uint64_t> sorted(allowed, allowed + allowed_count);
         std::sort(sorted.begin(), sorted.end());

@@ -122,6 +122,7 @@ struct frozen_index_t {
     device_buffer_t<uint64_t> allowed_keys; /* filtered search: sorted allowed keys and the bitmap built from them */
     device_buffer_t<uint32_t> allow_bits;
     uint32_t const* active_allow_bits = nullptr; /* set for the duration of one filtered call */
+    int active_cluster_end_level = -1;           /* set for the duration of one cluster() call */
     device_buffer_t<uint64_t> out_keys;
     device_buffer_t<float> out_dists;
     pinned_buffer_t<uint8_t> h_queries;
@@ -154,7 +155,7 @@ struct frozen_index_t {
     char const* search_host(void const* queries, size_t nq, size_t stride, uint32_t query_scalar, size_t k, uint64_t* keys,
                             size_t keys_stride, float* dists, size_t dists_stride, size_t* counts, uint64_t* computed,
                             uint64_t* cycles, size_t* total, uint64_t const* allowed = nullptr, size_t allowed_count = 0,
-                            bool filtered = false);
+                            bool filtered = false, int cluster_level = -1);
 };
 
 /* exact_kernel.cu */

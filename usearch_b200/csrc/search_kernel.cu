@@ -459,7 +459,9 @@ __device__ __forceinline__ void search_one(device_index_t const& ix, search_args
         computed += 1;
         float closest_d = cand_d[0];
         __syncwarp();
-        for (int level = ix.max_level; level > 0; --level) {
+        bool const cluster = a.cluster_end_level >= 0; /* index_gt::cluster (index.hpp:3092-3125): descent only */
+        int const end_level = cluster ? a.cluster_end_level : 0;
+        for (int level = ix.max_level; level > end_level; --level) {
             bool changed;
             do {
                 changed = false;
@@ -511,18 +513,19 @@ __device__ __forceinline__ void search_one(device_index_t const& ix, search_args
         computed += 1;
         float radius = cand_d[0];
         __syncwarp();
-        if (lane == 0) {
+        if (lane == 0 && !cluster) {
             heap.set_root(cand_t{radius, closest});
             if (bitmap) atomicOr(&visited[closest >> 5], 1u << (closest & 31));
             else atomicCAS(&visited[hash_slot(closest) & vmask], EMPTY_SLOT, closest);
             if (logged) vlog[0] = closest;
         }
-        heap_size = 1;
-        visited_count = 1;
+        heap_size = cluster ? 0 : 1;
+        visited_count = cluster ? 0 : 1;
         uint32_t pre_node = EMPTY_SLOT, pre_s0 = EMPTY_SLOT, pre_s1 = EMPTY_SLOT; /* speculative row prefetch */
         PHASE(pc0)
         {
-            bool allowed = slot_allowed(ix, a, closest);
+            /* cluster(): the closest member at that level is the whole answer, predicate ignored (index.hpp:3122) */
+            bool allowed = cluster || slot_allowed(ix, a, closest);
             if (allowed) {
                 if (topreg) {
                     if (lane == 0) { rtd[0] = radius; rts[0] = closest; }

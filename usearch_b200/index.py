@@ -48,7 +48,7 @@ EXPORTED_SYMBOLS = [
     "usearch_exact_search", "usearch_clear",
     # additive
     "usearch_search_many", "usearch_b200_search_many_device", "usearch_b200_search_many_stats",
-    "usearch_b200_filtered_search_many", "usearch_b200_exact_search_many",
+    "usearch_b200_filtered_search_many", "usearch_b200_exact_search_many", "usearch_b200_cluster_many",
     "usearch_b200_profile_phases", "usearch_b200_device", "usearch_b200_kernel_launches", "usearch_b200_last_kernel_ms",
     "usearch_b200_bytes_per_vector", "usearch_b200_max_level",
 ]
@@ -100,6 +100,9 @@ def load_library() -> C.CDLL:
     lib.usearch_b200_filtered_search_many.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int,
                                                       C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
                                                       C.c_void_p, C.c_void_p, C.c_void_p, err]
+    lib.usearch_b200_cluster_many.restype = None
+    lib.usearch_b200_cluster_many.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_size_t, C.c_void_p,
+                                              C.c_void_p, C.c_void_p, C.c_void_p, err]
     lib.usearch_b200_exact_search_many.restype = C.c_size_t
     lib.usearch_b200_exact_search_many.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_size_t,
                                                    C.c_void_p, C.c_void_p, C.c_void_p, err]
@@ -298,6 +301,33 @@ class Index:
     def filtered_search(self, vectors: np.ndarray, count: int, allowed_keys) -> Union[Matches, BatchMatches]:
         """`filtered_search` (index_dense.hpp:774-779) for the predicate "key in allowed_keys"."""
         return self.search(vectors, count, stats=True, _allowed=np.ascontiguousarray(allowed_keys, dtype=np.uint64))
+
+    def cluster(self, vectors: np.ndarray, level: int = 1, *, stats: bool = False):
+        """`index_dense_gt::cluster(vector, level)` (index_dense.hpp:788-793; index.hpp:3092-3125) for every row: the
+        closest member on graph level `level` (levels above the top return the entry point; 0 behaves like 1).
+        Returns `(keys [nq] u64, distances [nq] f32)`; with `stats=True` the counters land in `last_computed` /
+        `last_visited`."""
+        vectors = np.asarray(vectors)
+        if vectors.ndim == 1:
+            vectors = vectors[None, :]
+        if not vectors.flags.c_contiguous and vectors.strides[1] != vectors.itemsize:
+            vectors = np.ascontiguousarray(vectors)
+        kind = self._kind_of(vectors)
+        nq = vectors.shape[0]
+        keys = np.zeros(nq, dtype=np.uint64)
+        distances = np.zeros(nq, dtype=np.float32)
+        computed = np.zeros(nq, dtype=np.uint64)
+        visited = np.zeros(nq, dtype=np.uint64)
+        err = C.c_char_p()
+        self._lib.usearch_b200_cluster_many(
+            self._h, vectors.ctypes.data_as(C.c_void_p), nq, vectors.strides[0], SCALAR_KIND[kind], int(level),
+            keys.ctypes.data_as(C.c_void_p), distances.ctypes.data_as(C.c_void_p),
+            computed.ctypes.data_as(C.c_void_p) if stats else None, visited.ctypes.data_as(C.c_void_p) if stats else None,
+            C.byref(err))
+        _raise(err)
+        if stats:
+            self.last_computed, self.last_visited = computed, visited
+        return keys, distances
 
     def search(self, vectors: np.ndarray, count: int = 10, *, stats: bool = False, threads: int = 0, exact: bool = False,
                log=False, progress=None, _allowed: Optional[np.ndarray] = None) -> Union[Matches, BatchMatches]:
