@@ -21,6 +21,8 @@ INDEX_CASES = [
     ("hamming", "b1", 6000, 64, 20, 64, 100),    # 64-bit codes: ties everywhere
     ("tanimoto", "b1", 3000, 200, 10, 64, 0),
     ("sorensen", "b1", 3000, 256, 10, 64, 0),
+    ("l2sq", "f32", 1500, 2048, 10, 40, 30),     # 8 KB vectors: the tiled stage does not fit, one-query-per-warp scan kernel
+    ("cos", "f32", 20000, 64, 10, 300, 0),       # many tiles per segment, several query groups
 ]
 
 

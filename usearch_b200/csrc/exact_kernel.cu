@@ -15,13 +15,24 @@
  *  Distances are computed by the very metric structs of the search kernel (metrics.cuh): one (query, vector)
  *  pair yields the same bits in both kernels.
  *
- *  Work layout: a CTA owns W queries (one warp each, query in shared memory) and one segment of the dataset;
- *  thread 0 streams tiles of VPP vectors into a double-buffered shared-memory stage with TMA bulk copies and
- *  all W warps reduce every tile against their own query, so each vector is fetched once per W queries.
+ *  Two scan kernels share the partial-list format and the merge:
+ *
+ *  exact_tiled_kernel (the default): the scan is FFMA/LDS-bound, not HBM-bound (1M x 768 f32 against 4096 queries
+ *  is 3.1e12 multiply-adds but only 3 GB of vectors), so the work is register-tiled like an SGEMM whose inner
+ *  product keeps the reference's summation order: a CTA owns 8 warps x QT queries (in shared memory) and one
+ *  segment of the dataset; warp 0 streams tiles of TV vectors into a double-buffered stage with per-lane TMA bulk
+ *  copies; every lane group (LPV lanes) reduces VT vectors of the tile against the QT queries of its warp, all
+ *  QT x VT accumulator sets in registers: one stage read feeds QT pairs and one (broadcast) query read feeds VT x 8
+ *  groups. The k-best lists live in global memory (L2): after the first few tiles an insertion is a rare event.
+ *
+ *  exact_scan_kernel (fallback when the tiled stage does not fit in 227 KB): one query per warp, list in registers.
  */
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
 #include <type_traits>
 
 #include "device_index.h"
@@ -46,10 +57,18 @@ struct exact_args_t {
     uint32_t* out_counts = nullptr;
     uint32_t stage_stride = 0, off_bars = 0, off_stage = 0;
     uint32_t slots_as_keys = 0;             /* 1: report the slot number as the key (free-function mode) */
+    uint32_t off_queries = 0;               /* tiled kernel: queries region precedes the barriers */
 };
 
 template <class M, class = void> struct has_finish_sw : std::false_type {};
 template <class M> struct has_finish_sw<M, decltype((void)&M::finish_sw, void())> : std::true_type {};
+
+/* reciprocal norms (metrics with NORMS): computed once per query and once per stored vector of a tile */
+template <class M, bool = M::NORMS> struct rnorm_of { using type = float; static __device__ __forceinline__ type get(float) { return 0.f; } };
+template <class M> struct rnorm_of<M, true> {
+    using type = typename M::rn_t;
+    static __device__ __forceinline__ type get(float x2) { return M::rnorm(x2); }
+};
 
 template <class M, bool SWAP>
 __device__ __forceinline__ float finish_ordered(typename M::acc_t const& acc, typename M::qconst_t qc) {
@@ -83,6 +102,8 @@ __global__ void __launch_bounds__(EXACT_WARPS * 32) exact_scan_kernel(__grid_con
     }
     __syncthreads();
     typename M::qconst_t qc = M::prepare(q4, chunks, lane);
+    typename rnorm_of<M>::type q_rn = 0;
+    if constexpr (M::NORMS) q_rn = rnorm_of<M>::get(qc.a2);
 
     auto issue = [&](uint32_t t) { /* thread 0 only */
         uint32_t const base = seg_lo + t * VPP, cnt = min((uint32_t)VPP, seg_hi - base), set = t & 1u;
@@ -125,7 +146,8 @@ __global__ void __launch_bounds__(EXACT_WARPS * 32) exact_scan_kernel(__grid_con
         float d = finish_ordered<M, SWAP>(acc, qc);
         if constexpr (M::NORMS) {
             float const b2 = act ? __ldg(ix.norms + slot) : 0.f;
-            d = SWAP ? M::finalize_sw(d, qc, b2) : M::finalize(d, qc, b2);
+            auto const v_rn = rnorm_of<M>::get(b2);
+            d = SWAP ? M::finalize_rn(d, b2, qc.a2, v_rn, q_rn) : M::finalize_rn(d, qc.a2, b2, q_rn, v_rn);
         }
         bool keep = act && sub == 0;
         if (keep && ix.deleted_bits) keep = !((ix.deleted_bits[slot >> 5] >> (slot & 31)) & 1u);
@@ -153,6 +175,171 @@ __global__ void __launch_bounds__(EXACT_WARPS * 32) exact_scan_kernel(__grid_con
             if (i < top_size) { a.part_d[row + i] = td[j]; a.part_s[row + i] = ts[j]; }
         }
         if (lane == 0) a.part_n[(size_t)qi * a.segments + blockIdx.y] = top_size;
+    }
+}
+
+/* ---- register-tiled scan ------------------------------------------------------------------------------------- */
+
+constexpr int TILED_WARPS = 8; /* two per scheduler: one warp alone leaves half of the issue slots idle (ncu) */
+
+template <class M> struct exact_tile_t {
+    static constexpr int QT = M::LPV == 4 ? 4 : 8;  /* queries per warp */
+    static constexpr int VT = M::LPV == 4 ? 2 : 1;  /* vectors per lane group and tile */
+    static constexpr int TV = (32 / M::LPV) * VT;   /* vectors per tile */
+    static constexpr int QPC = TILED_WARPS * QT;    /* queries per CTA */
+};
+
+/* sorted insert into a k-best list in global memory under (distance asc, slot desc); whole warp, uniform arguments */
+__device__ __forceinline__ void top_insert_global_keyed(float volatile* ld, uint32_t volatile* ls, uint32_t& size, uint32_t k, float cd,
+                                                        uint32_t cs, int lane) {
+    uint32_t pos = 0;
+    for (uint32_t base = 0; base < size; base += 32) {
+        uint32_t const i = base + (uint32_t)lane;
+        bool before = false;
+        if (i < size) {
+            float const d = ld[i];
+            before = d < cd || (d == cd && ls[i] > cs);
+        }
+        pos += __popc(__ballot_sync(0xffffffffu, before));
+    }
+    if (pos >= k) return;
+    uint32_t const new_size = size < k ? size + 1 : k;
+    for (int hi = (int)new_size - 1; hi > (int)pos; hi -= 32) { /* old [pos, new_size-1) moves one to the right, tail first */
+        int const i = hi - lane;
+        bool const mv = i > (int)pos;
+        float d = 0.f;
+        uint32_t sl = 0;
+        if (mv) { d = ld[i - 1]; sl = ls[i - 1]; }
+        __syncwarp();
+        if (mv) { ld[i] = d; ls[i] = sl; }
+        __syncwarp();
+    }
+    if (lane == 0) { ld[pos] = cd; ls[pos] = cs; }
+    __syncwarp();
+    size = new_size;
+}
+
+template <class M, bool SWAP>
+__global__ void __launch_bounds__(TILED_WARPS * 32, 1) exact_tiled_kernel(__grid_constant__ device_index_t const ix,
+                                                                          __grid_constant__ exact_args_t const a) {
+    using T = exact_tile_t<M>;
+    constexpr int LPV = M::LPV, QT = T::QT, VT = T::VT, TV = T::TV, GROUPS = 32 / LPV;
+    extern __shared__ __align__(128) uint8_t smem[];
+    int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane / LPV, sub = lane % LPV;
+    uint32_t const chunks = ix.chunks16, bytes = (uint32_t)ix.vec_stride;
+    uint32_t const bars = smem_u32(smem + a.off_bars), stage_addr = smem_u32(smem + a.off_stage);
+    uint32_t const q0 = blockIdx.x * T::QPC + (uint32_t)warp * QT; /* first query of this warp */
+    uint32_t const seg_lo = blockIdx.y * a.segment_len, seg_hi = min(ix.n, seg_lo + a.segment_len);
+    uint32_t const ntiles = seg_hi > seg_lo ? (seg_hi - seg_lo + TV - 1) / TV : 0;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bars, 1);
+        mbar_init(bars + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    uint4 const* qrow[QT];
+#pragma unroll
+    for (int qi = 0; qi < QT; ++qi) {
+        uint4* dst = reinterpret_cast<uint4*>(smem + a.off_queries + (size_t)(warp * QT + qi) * bytes);
+        qrow[qi] = dst;
+        bool const live = q0 + qi < a.nq;
+        uint4 const* src = reinterpret_cast<uint4 const*>(a.queries + (size_t)(live ? q0 + qi : 0) * a.query_stride);
+        for (uint32_t j = lane; j < chunks; j += 32) dst[j] = live ? src[j] : make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncthreads();
+    typename M::qconst_t qc[QT];
+#pragma unroll
+    for (int qi = 0; qi < QT; ++qi) qc[qi] = M::prepare(qrow[qi], chunks, lane);
+    typename rnorm_of<M>::type q_rn[QT];
+#pragma unroll
+    for (int qi = 0; qi < QT; ++qi) {
+        q_rn[qi] = 0;
+        if constexpr (M::NORMS) q_rn[qi] = rnorm_of<M>::get(qc[qi].a2);
+    }
+
+    auto issue = [&](uint32_t t) { /* warp 0: lane i fetches vector i of the tile */
+        uint32_t const base = seg_lo + t * TV, cnt = min((uint32_t)TV, seg_hi - base), set = t & 1u;
+        if (lane == 0) mbar_expect_tx(bars + 8u * set, cnt * bytes);
+        __syncwarp();
+        for (uint32_t i = lane; i < cnt; i += 32)
+            bulk_copy_g2s(stage_addr + (set * TV + i) * a.stage_stride, ix.vectors + (size_t)(base + i) * ix.vec_stride, bytes,
+                          bars + 8u * set);
+    };
+    if (warp == 0 && ntiles) issue(0);
+
+    uint32_t sizes[QT];
+    float worst[QT];
+#pragma unroll
+    for (int qi = 0; qi < QT; ++qi) { sizes[qi] = 0; worst[qi] = 0.f; }
+    uint32_t phase = 0;
+
+    for (uint32_t t = 0; t < ntiles; ++t) {
+        uint32_t const set = t & 1u, base = seg_lo + t * TV, cnt = min((uint32_t)TV, seg_hi - base);
+        if (warp == 0 && t + 1 < ntiles) issue(t + 1); /* the other set was released by the barrier below */
+        mbar_wait(bars + 8u * set, (phase >> set) & 1u);
+        phase ^= 1u << set;
+
+        typename M::acc_t acc[QT][VT];
+#pragma unroll
+        for (int qi = 0; qi < QT; ++qi)
+#pragma unroll
+            for (int vt = 0; vt < VT; ++vt) M::init(acc[qi][vt]);
+        uint4 const* vrow[VT];
+#pragma unroll
+        for (int vt = 0; vt < VT; ++vt) /* a short last tile reads stale stage rows: results are discarded below */
+            vrow[vt] = reinterpret_cast<uint4 const*>(smem + a.off_stage + (size_t)(set * TV + vt * GROUPS + g) * a.stage_stride);
+#pragma unroll 2
+        for (uint32_t j = sub; j < chunks; j += LPV) {
+            uint4 b[VT];
+#pragma unroll
+            for (int vt = 0; vt < VT; ++vt) b[vt] = vrow[vt][j];
+#pragma unroll
+            for (int qi = 0; qi < QT; ++qi) {
+                uint4 const q = qrow[qi][j];
+#pragma unroll
+                for (int vt = 0; vt < VT; ++vt) M::step(acc[qi][vt], b[vt], q);
+            }
+        }
+
+#pragma unroll
+        for (int vt = 0; vt < VT; ++vt) {
+            uint32_t const in_tile = (uint32_t)(vt * GROUPS + g), slot = base + in_tile;
+            bool usable = in_tile < cnt;
+            float b2 = 0.f;
+            if constexpr (M::NORMS) b2 = usable ? __ldg(ix.norms + slot) : 0.f;
+            auto const v_rn = rnorm_of<M>::get(b2);
+            if (usable && ix.deleted_bits) usable = !((ix.deleted_bits[slot >> 5] >> (slot & 31)) & 1u);
+            usable = usable && sub == 0;
+#pragma unroll
+            for (int qi = 0; qi < QT; ++qi) {
+                float d = finish_ordered<M, SWAP>(acc[qi][vt], qc[qi]);
+                if constexpr (M::NORMS)
+                    d = SWAP ? M::finalize_rn(d, b2, qc[qi].a2, v_rn, q_rn[qi]) : M::finalize_rn(d, qc[qi].a2, b2, q_rn[qi], v_rn);
+                bool const live = q0 + qi < a.nq;
+                uint32_t todo = __ballot_sync(0xffffffffu, usable && live && (sizes[qi] < a.k || !(d > worst[qi])));
+                if (todo) {
+                    size_t const row = ((size_t)(q0 + qi) * a.segments + blockIdx.y) * a.k;
+                    while (todo) {
+                        int const src_lane = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        float const cd = __shfl_sync(0xffffffffu, d, src_lane);
+                        uint32_t const cs = base + (uint32_t)(vt * GROUPS + src_lane / LPV);
+                        if (sizes[qi] < a.k || !(cd > worst[qi])) {
+                            top_insert_global_keyed(a.part_d + row, a.part_s + row, sizes[qi], a.k, cd, cs, lane);
+                            if (sizes[qi] == a.k) worst[qi] = reinterpret_cast<float volatile*>(a.part_d)[row + a.k - 1];
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads(); /* every warp is done with this set before warp 0 refills it */
+    }
+
+    if (lane == 0) {
+#pragma unroll
+        for (int qi = 0; qi < QT; ++qi)
+            if (q0 + qi < a.nq) a.part_n[(size_t)(q0 + qi) * a.segments + blockIdx.y] = sizes[qi];
     }
 }
 
@@ -202,6 +389,25 @@ template <class M> static cudaError_t exact_launch_t(device_index_t const& ix, e
     return cudaGetLastError();
 }
 
+template <class M> static cudaError_t exact_launch_tiled_t(device_index_t const& ix, exact_args_t const& a, bool swap, dim3 grid, size_t smem,
+                                                           cudaStream_t stream) {
+    if (swap) {
+        cudaError_t e = cudaFuncSetAttribute(exact_tiled_kernel<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        exact_tiled_kernel<M, true><<<grid, TILED_WARPS * 32, smem, stream>>>(ix, a);
+    } else {
+        cudaError_t e = cudaFuncSetAttribute(exact_tiled_kernel<M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        exact_tiled_kernel<M, false><<<grid, TILED_WARPS * 32, smem, stream>>>(ix, a);
+    }
+    return cudaGetLastError();
+}
+
+template <class M> static cudaError_t exact_launch_any_t(bool tiled, device_index_t const& ix, exact_args_t const& a, bool swap, dim3 grid,
+                                                         size_t smem, cudaStream_t stream) {
+    return tiled ? exact_launch_tiled_t<M>(ix, a, swap, grid, smem, stream) : exact_launch_t<M>(ix, a, swap, grid, smem, stream);
+}
+
 static int exact_lpv(device_index_t const& ix) {
     if (ix.scalar == SCALAR_F16 || ix.scalar == SCALAR_BF16) return 1;
     if (ix.scalar == SCALAR_B1) return 2;
@@ -224,7 +430,7 @@ char const* exact_search_device(device_index_t const& ix, int sm_count, void con
         if (cudaMemsetAsync(d_dists, 0xFF, nq * k * 4, stream) != cudaSuccess) return "CUDA failure: memset"; /* NaN */
         return nullptr;
     }
-    int const lpv = exact_lpv(ix), vpp = 32 / lpv;
+    int const lpv = exact_lpv(ix);
     exact_args_t a;
     a.queries = static_cast<uint8_t const*>(d_queries);
     a.query_stride = query_stride;
@@ -232,17 +438,41 @@ char const* exact_search_device(device_index_t const& ix, int sm_count, void con
     a.k = (uint32_t)k;
     a.slots_as_keys = slots_as_keys ? 1u : 0u;
     a.stage_stride = (uint32_t)((ix.vec_stride + 127) / 128 * 128) + 16u * (uint32_t)lpv;
-    uint32_t off = EXACT_WARPS * (uint32_t)ix.vec_stride;
+    /* the register-tiled kernel when its stage fits; USEARCH_B200_EXACT=scan|tiled forces one (tests) */
+    int const qt = lpv == 4 ? 4 : 8, tile_vectors = (32 / lpv) * (lpv == 4 ? 2 : 1), qpc_tiled = TILED_WARPS * qt;
+    size_t const tiled_smem = ((size_t)qpc_tiled * ix.vec_stride + 16 + 127) / 128 * 128 + 2 * (size_t)tile_vectors * a.stage_stride;
+    static int const forced = [] {
+        char const* v = std::getenv("USEARCH_B200_EXACT");
+        return !v ? 0 : (std::strcmp(v, "scan") == 0 ? 1 : (std::strcmp(v, "tiled") == 0 ? 2 : 0));
+    }();
+    bool const tiled = forced == 1 ? false : tiled_smem <= 227 * 1024;
+    if (forced == 2 && !tiled) return "Vectors too long for the tiled exact-search stage";
+    int const vpp = tiled ? tile_vectors : 32 / lpv;       /* vectors per tile */
+    uint32_t const qpc = tiled ? (uint32_t)qpc_tiled : (uint32_t)EXACT_WARPS;
+    uint32_t off = qpc * (uint32_t)ix.vec_stride;
+    a.off_queries = 0;
     a.off_bars = off;
     off = (off + 16 + 127) / 128 * 128;
     a.off_stage = off;
     size_t const smem = off + 2 * (size_t)vpp * a.stage_stride;
     if (smem > 227 * 1024) return "Vectors too long for the exact-search stage";
-    uint32_t const groups = (uint32_t)((nq + EXACT_WARPS - 1) / EXACT_WARPS);
-    uint32_t want_ctas = (uint32_t)sm_count * 3;
-    uint32_t segments = groups >= want_ctas ? 1u : (want_ctas + groups - 1) / groups;
-    uint32_t const max_segments = std::max<uint32_t>(1, (ix.n + 4 * (uint32_t)vpp - 1) / (4 * (uint32_t)vpp));
-    segments = std::min(std::min(segments, max_segments), 65535u);
+    uint32_t const groups = (uint32_t)((nq + qpc - 1) / qpc);
+    /* cut the dataset so that the grid fills whole waves of the resident CTAs (1 per SM tiled, ~3 per SM otherwise) */
+    uint32_t const resident = (uint32_t)sm_count * (tiled ? 1u : 3u);
+    uint32_t const max_segments = std::max<uint32_t>(1, std::min<uint32_t>((ix.n + 8 * (uint32_t)vpp - 1) / (8 * (uint32_t)vpp), 65535u));
+    uint32_t segments = 1;
+    {
+        double best = -1;
+        uint32_t const lo = std::max<uint32_t>(1, (resident + groups - 1) / groups);
+        for (uint32_t s = lo; s <= lo + 24; ++s) {
+            uint32_t const c = std::min(s, max_segments);
+            double const total = (double)groups * c, waves = std::ceil(total / resident);
+            double const util = total / (waves * resident) - 0.002 * c; /* prefer fewer segments on a tie */
+            if (util > best) { best = util; segments = c; }
+        }
+    }
+    size_t const list_bytes = nq * k * 8;
+    while (segments > 1 && list_bytes * segments > ((size_t)1 << 30)) --segments;
     uint32_t seg_len = (ix.n + segments - 1) / segments;
     seg_len = (seg_len + (uint32_t)vpp - 1) / (uint32_t)vpp * (uint32_t)vpp;
     segments = (ix.n + seg_len - 1) / seg_len;
@@ -261,29 +491,29 @@ char const* exact_search_device(device_index_t const& ix, int sm_count, void con
     cudaError_t e = cudaErrorInvalidValue;
     switch (ix.scalar) {
     case SCALAR_F32:
-        if (ix.metric == METRIC_L2SQ) e = exact_launch_t<l2sq_f32_t>(ix, a, swap, grid, smem, stream);
-        else if (ix.metric == METRIC_IP) e = exact_launch_t<ip_f32_t>(ix, a, swap, grid, smem, stream);
-        else if (ix.metric == METRIC_COS) e = exact_launch_t<cos_f32_t>(ix, a, swap, grid, smem, stream);
+        if (ix.metric == METRIC_L2SQ) e = exact_launch_any_t<l2sq_f32_t>(tiled, ix, a, swap, grid, smem, stream);
+        else if (ix.metric == METRIC_IP) e = exact_launch_any_t<ip_f32_t>(tiled, ix, a, swap, grid, smem, stream);
+        else if (ix.metric == METRIC_COS) e = exact_launch_any_t<cos_f32_t>(tiled, ix, a, swap, grid, smem, stream);
         break;
     case SCALAR_F16:
-        if (ix.metric == METRIC_L2SQ) e = exact_launch_t<l2sq_half_t<f16_conv_t>>(ix, a, swap, grid, smem, stream);
-        else if (ix.metric == METRIC_IP) e = exact_launch_t<ip_half_t<f16_conv_t>>(ix, a, swap, grid, smem, stream);
-        else if (ix.metric == METRIC_COS) e = exact_launch_t<cos_half_t<f16_conv_t>>(ix, a, swap, grid, smem, stream);
+        if (ix.metric == METRIC_L2SQ) e = exact_launch_any_t<l2sq_half_t<f16_conv_t>>(tiled, ix, a, swap, grid, smem, stream);
+        else if (ix.metric == METRIC_IP) e = exact_launch_any_t<ip_half_t<f16_conv_t>>(tiled, ix, a, swap, grid, smem, stream);
+        else if (ix.metric == METRIC_COS) e = exact_launch_any_t<cos_half_t<f16_conv_t>>(tiled, ix, a, swap, grid, smem, stream);
         break;
     case SCALAR_BF16:
-        if (ix.metric == METRIC_L2SQ) e = exact_launch_t<l2sq_half_t<bf16_conv_t>>(ix, a, swap, grid, smem, stream);
-        else if (ix.metric == METRIC_IP) e = exact_launch_t<ip_half_t<bf16_conv_t>>(ix, a, swap, grid, smem, stream);
-        else if (ix.metric == METRIC_COS) e = exact_launch_t<cos_half_t<bf16_conv_t>>(ix, a, swap, grid, smem, stream);
+        if (ix.metric == METRIC_L2SQ) e = exact_launch_any_t<l2sq_half_t<bf16_conv_t>>(tiled, ix, a, swap, grid, smem, stream);
+        else if (ix.metric == METRIC_IP) e = exact_launch_any_t<ip_half_t<bf16_conv_t>>(tiled, ix, a, swap, grid, smem, stream);
+        else if (ix.metric == METRIC_COS) e = exact_launch_any_t<cos_half_t<bf16_conv_t>>(tiled, ix, a, swap, grid, smem, stream);
         break;
     case SCALAR_I8:
-        if (ix.metric == METRIC_L2SQ) e = exact_launch_t<l2sq_i8_t<4>>(ix, a, swap, grid, smem, stream);
-        else if (ix.metric == METRIC_IP) e = exact_launch_t<ip_i8_t<4>>(ix, a, swap, grid, smem, stream);
-        else if (ix.metric == METRIC_COS) e = exact_launch_t<cos_i8_t<4>>(ix, a, swap, grid, smem, stream);
+        if (ix.metric == METRIC_L2SQ) e = exact_launch_any_t<l2sq_i8_t<4>>(tiled, ix, a, swap, grid, smem, stream);
+        else if (ix.metric == METRIC_IP) e = exact_launch_any_t<ip_i8_t<4>>(tiled, ix, a, swap, grid, smem, stream);
+        else if (ix.metric == METRIC_COS) e = exact_launch_any_t<cos_i8_t<4>>(tiled, ix, a, swap, grid, smem, stream);
         break;
     case SCALAR_B1:
-        if (ix.metric == METRIC_HAMMING) e = exact_launch_t<hamming_b1_t<2>>(ix, a, swap, grid, smem, stream);
-        else if (ix.metric == METRIC_TANIMOTO || ix.metric == METRIC_JACCARD) e = exact_launch_t<tanimoto_b1_t<2>>(ix, a, swap, grid, smem, stream);
-        else if (ix.metric == METRIC_SORENSEN) e = exact_launch_t<sorensen_b1_t<2>>(ix, a, swap, grid, smem, stream);
+        if (ix.metric == METRIC_HAMMING) e = exact_launch_any_t<hamming_b1_t<2>>(tiled, ix, a, swap, grid, smem, stream);
+        else if (ix.metric == METRIC_TANIMOTO || ix.metric == METRIC_JACCARD) e = exact_launch_any_t<tanimoto_b1_t<2>>(tiled, ix, a, swap, grid, smem, stream);
+        else if (ix.metric == METRIC_SORENSEN) e = exact_launch_any_t<sorensen_b1_t<2>>(tiled, ix, a, swap, grid, smem, stream);
         break;
     default: break;
     }

@@ -136,6 +136,16 @@ struct cos_f32_t {
     static __device__ __forceinline__ float finalize(float ab, qconst_t qc, float b2) { return cos_normalize_f64(ab, qc.a2, b2); }
     /* metric(stored, query) instead of metric(query, stored): exact_search_t calls it that way (index_plugins.hpp:2112) */
     static __device__ __forceinline__ float finalize_sw(float ab, qconst_t qc, float b2) { return cos_normalize_f64(ab, b2, qc.a2); }
+    /* the two reciprocal roots of cos_normalize_f64 depend on one operand each: a dense scan computes them once per
+     * query / per stored vector and finishes every pair with two multiplies — same operations, same bits */
+    using rn_t = double;
+    static __device__ __forceinline__ rn_t rnorm(float x2) { return __drcp_rn(__dsqrt_rn((double)x2)); }
+    static __device__ __forceinline__ float finalize_rn(float ab, float first2, float second2, rn_t rfirst, rn_t rsecond) {
+        if (first2 == 0.f && second2 == 0.f) return 0.f;
+        if (ab == 0.f) return 1.f;
+        double r = __dsub_rn(1.0, __dmul_rn(__dmul_rn((double)ab, rfirst), rsecond));
+        return r > 0 ? __double2float_rn(r) : 0.f;
+    }
     /* dot(v, v) in the 16-accumulator order; every 4-lane group computes the same value */
     static __device__ __forceinline__ float self_dot(uint4 const* v4, uint32_t chunks16, int lane) {
         float v[4] = {0.f, 0.f, 0.f, 0.f};
@@ -261,6 +271,14 @@ template <class C> struct cos_half_t {
     static __device__ __forceinline__ float finish(acc_t const& a, qconst_t) { return __double2float_rn(reduce8_f64(a.v)); }
     static __device__ __forceinline__ float finalize(float ab, qconst_t qc, float b2) { return cos_normalize_f32(ab, qc.a2, b2); }
     static __device__ __forceinline__ float finalize_sw(float ab, qconst_t qc, float b2) { return cos_normalize_f32(ab, b2, qc.a2); }
+    using rn_t = float;
+    static __device__ __forceinline__ rn_t rnorm(float x2) { return __frcp_rn(__fsqrt_rn(x2)); }
+    static __device__ __forceinline__ float finalize_rn(float ab, float first2, float second2, rn_t rfirst, rn_t rsecond) {
+        if (first2 == 0.0f && second2 == 0.0f) return 0.0f;
+        if (ab == 0.0f) return 1.0f;
+        float r = __fsub_rn(1.0f, __fmul_rn(__fmul_rn(ab, rfirst), rsecond));
+        return r > 0 ? r : 0.f;
+    }
     static __device__ __forceinline__ float self_dot(uint4 const* v4, uint32_t chunks16, int) {
         float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         for (uint32_t j = 0; j < chunks16; ++j) {
