@@ -778,22 +778,9 @@ char const* frozen_index_t::search_host(void const* q, size_t nq, size_t stride,
     return nullptr;
 }
 
-} // namespace usearch_b200
-
-
-namespace usearch_b200 {
-
-namespace {
-char const* cuda_error2(cudaError_t e) {
-    if (e == cudaSuccess) return nullptr;
-    cudaGetLastError();
-    return e == cudaErrorMemoryAllocation ? "Out of GPU memory!" : "CUDA failure in exact search";
-}
-#define CU2(call)                                               \
-    do {                                                        \
-        if (char const* err_ = cuda_error2((call))) return err_; \
-    } while (0)
-} // namespace
+/* ---------------------------------------------------------------------------------------------- */
+/*  exact (brute-force) search: host wrappers around exact_kernel.cu                              */
+/* ---------------------------------------------------------------------------------------------- */
 
 /* index_gt::search(exact = true) (index.hpp:3047-3051 -> search_exact_ :4251-4268) for a batch of host queries */
 char const* frozen_index_t::exact_host(void const* q, size_t nq, size_t stride, uint32_t query_scalar, size_t k, uint64_t* keys,
@@ -807,22 +794,22 @@ char const* frozen_index_t::exact_host(void const* q, size_t nq, size_t stride, 
     if (char const* e = out_keys.reserve(nq * k)) return e;
     if (char const* e = out_dists.reserve(nq * k)) return e;
     if (char const* e = counts_reserve_all(nq)) return e;
-    if (vs != bpv) CU2(cudaMemsetAsync(queries.ptr, 0, nq * vs, stream));
+    if (vs != bpv) CU(cudaMemsetAsync(queries.ptr, 0, nq * vs, stream));
     if (query_scalar == scalar) {
-        CU2(cudaMemcpy2DAsync(queries.ptr, vs, q, stride, bpv, nq, cudaMemcpyHostToDevice, stream));
+        CU(cudaMemcpy2DAsync(queries.ptr, vs, q, stride, bpv, nq, cudaMemcpyHostToDevice, stream));
     } else {
         if (char const* e = h_queries.reserve(nq * vs)) return e;
         if (char const* e = cast_queries(query_scalar, scalar, dimensions, static_cast<uint8_t const*>(q), stride, nq, h_queries.ptr, vs)) return e;
-        CU2(cudaMemcpy2DAsync(queries.ptr, vs, h_queries.ptr, vs, bpv, nq, cudaMemcpyHostToDevice, stream));
+        CU(cudaMemcpy2DAsync(queries.ptr, vs, h_queries.ptr, vs, bpv, nq, cudaMemcpyHostToDevice, stream));
     }
     if (char const* e = exact_search_device(d, sm_count, queries.ptr, nq, vs, k, false, false, out_keys.ptr, out_dists.ptr, counts.ptr,
                                             exact_scratch, stream))
         return e;
     kernel_launches += 2;
-    CU2(cudaMemcpyAsync(keys, out_keys.ptr, nq * k * 8, cudaMemcpyDeviceToHost, stream));
-    CU2(cudaMemcpyAsync(dists, out_dists.ptr, nq * k * 4, cudaMemcpyDeviceToHost, stream));
-    CU2(cudaMemcpyAsync(h_counts.ptr, counts.ptr, nq * 4, cudaMemcpyDeviceToHost, stream));
-    CU2(cudaStreamSynchronize(stream));
+    CU(cudaMemcpyAsync(keys, out_keys.ptr, nq * k * 8, cudaMemcpyDeviceToHost, stream));
+    CU(cudaMemcpyAsync(dists, out_dists.ptr, nq * k * 4, cudaMemcpyDeviceToHost, stream));
+    CU(cudaMemcpyAsync(h_counts.ptr, counts.ptr, nq * 4, cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
     if (counts_out)
         for (size_t i = 0; i < nq; ++i) counts_out[i] = h_counts.ptr[i];
     return nullptr;
@@ -863,23 +850,23 @@ char const* exact_search_free(void const* dataset, size_t n, size_t dataset_stri
     if (char const* e = d_counts.reserve(nq)) return e;
     cudaStream_t s = tmp.stream;
     if (vs != bpv) {
-        CU2(cudaMemsetAsync(d_vectors.ptr, 0, n * vs, s));
-        CU2(cudaMemsetAsync(d_queries.ptr, 0, nq * vs, s));
+        CU(cudaMemsetAsync(d_vectors.ptr, 0, n * vs, s));
+        CU(cudaMemsetAsync(d_queries.ptr, 0, nq * vs, s));
     }
-    CU2(cudaMemcpy2DAsync(d_vectors.ptr, vs, dataset, dataset_stride, bpv, n, cudaMemcpyHostToDevice, s));
-    CU2(cudaMemcpy2DAsync(d_queries.ptr, vs, queries_h, queries_stride, bpv, nq, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpy2DAsync(d_vectors.ptr, vs, dataset, dataset_stride, bpv, n, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpy2DAsync(d_queries.ptr, vs, queries_h, queries_stride, bpv, nq, cudaMemcpyHostToDevice, s));
     ix.vectors = d_vectors.ptr;
     if (search_needs_norms(metric, scalar)) {
         if (char const* e = d_norms.reserve(n)) return e;
-        CU2(search_compute_norms(ix, d_norms.ptr, s));
+        CU(search_compute_norms(ix, d_norms.ptr, s));
         ix.norms = d_norms.ptr;
     }
     if (char const* e = exact_search_device(ix, tmp.sm_count, d_queries.ptr, nq, vs, k, true, true, d_keys.ptr, d_dists.ptr, d_counts.ptr,
                                             scratch, s))
         return e;
-    CU2(cudaMemcpy2DAsync(keys, keys_stride, d_keys.ptr, k * 8, k * 8, nq, cudaMemcpyDeviceToHost, s));
-    CU2(cudaMemcpy2DAsync(distances, distances_stride, d_dists.ptr, k * 4, k * 4, nq, cudaMemcpyDeviceToHost, s));
-    CU2(cudaStreamSynchronize(s));
+    CU(cudaMemcpy2DAsync(keys, keys_stride, d_keys.ptr, k * 8, k * 8, nq, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpy2DAsync(distances, distances_stride, d_dists.ptr, k * 4, k * 4, nq, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
     return nullptr;
 }
 
