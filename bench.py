@@ -259,6 +259,71 @@ def run_reference_arm(a):
 #  our arm
 # ------------------------------------------------------------------------------------------------
 
+def measure_next_rows(a, index, ref, batch: np.ndarray, k: int, threads: int) -> dict:
+    """SURVEY §8(f) rows on the bench collection, outside the timed region of the headline metric: wall clock of one
+    call through the host API for the whole batch, the reference timed on a bounded sample of the same batch, and
+    label agreement on that sample. Never raises: a failure is reported in the JSON instead of losing the line."""
+    out = {}
+    try:
+        index.search(batch[:256], k, exact=True)  # warm-up (scratch allocation)
+        t0 = time.perf_counter()
+        exact = index.search(batch, k, exact=True)
+        dt = time.perf_counter() - t0
+        sample = batch[:max(4 * threads, 64)]
+        t0 = time.perf_counter()
+        want = ref.search(sample, k, threads=threads, exact=True)
+        dt_cpu = time.perf_counter() - t0
+        out["exact_search"] = {
+            "value": round(len(batch) / dt, 1), "unit": "queries/s", "ms_per_batch": round(dt * 1e3, 1),
+            "multiply_adds_per_s": round(len(batch) * index.size * a.dim / dt / 1e12, 2), "multiply_adds_unit": "T/s",
+            "cpu_reference": {"value": round(len(sample) / dt_cpu, 1), "unit": "queries/s", "cores": threads,
+                              "sample": f"{len(sample)} queries in {dt_cpu:.1f} s, index.search(exact=True)"},
+            "rows_with_identical_labels": round(float((want[0] == exact.keys[:len(sample)]).all(axis=1).mean()), 4),
+        }
+    except Exception as e:  # noqa: BLE001
+        out["exact_search"] = {"error": str(e)}
+    try:
+        level = 1
+        index.cluster(batch[:256], level)
+        t0 = time.perf_counter()
+        gk, gd = index.cluster(batch, level, stats=True)
+        dt = time.perf_counter() - t0
+        sample = batch[:1024]
+        t0 = time.perf_counter()
+        wk, wd, wc, wv = ref.cluster(sample, level)
+        dt_cpu = time.perf_counter() - t0
+        out["cluster"] = {
+            "value": round(len(batch) / dt, 1), "unit": "queries/s", "level": level, "ms_per_batch": round(dt * 1e3, 2),
+            "cpu_reference": {"value": round(len(sample) / dt_cpu, 1), "unit": "queries/s", "cores": 1,
+                              "sample": f"{len(sample)} queries in {dt_cpu:.2f} s, index.cluster(vector, {level})"},
+            "rows_with_identical_members": round(float((wk == gk[:len(sample)]).mean()), 4),
+            "counters_identical": bool(np.array_equal(wc, index.last_computed[:len(sample)])),
+        }
+    except Exception as e:  # noqa: BLE001
+        out["cluster"] = {"error": str(e)}
+    try:
+        allowed = np.arange(0, index.size, 10, dtype=np.uint64)  # one key in ten passes the predicate
+        index.filtered_search(batch[:256], k, allowed)
+        t0 = time.perf_counter()
+        got = index.filtered_search(batch, k, allowed)
+        dt = time.perf_counter() - t0
+        sample = batch[:512].astype(np.float32) if batch.dtype != np.float32 else batch[:512]
+        row = {"value": round(len(batch) / dt, 1), "unit": "queries/s", "ms_per_batch": round(dt * 1e3, 2),
+               "predicate": "key % 10 == 0 (bitmap over slots built on the device from the sorted key list)",
+               "all_labels_pass_predicate": bool((got.keys[got.distances == got.distances] % 10 == 0).all())}
+        if a.dtype == "f32":
+            t0 = time.perf_counter()
+            want = ref.filtered_search(sample, k, allowed, threads=threads)
+            dt_cpu = time.perf_counter() - t0
+            row["cpu_reference"] = {"value": round(len(sample) / dt_cpu, 1), "unit": "queries/s", "cores": threads,
+                                    "sample": f"{len(sample)} queries in {dt_cpu:.2f} s, filtered_search"}
+            row["rows_with_identical_labels"] = round(float((want[0] == got.keys[:len(sample)]).all(axis=1).mean()), 4)
+        out["filtered_search"] = row
+    except Exception as e:  # noqa: BLE001
+        out["filtered_search"] = {"error": str(e)}
+    return out
+
+
 def run_b200_arm(a):
     import torch
     import torch.distributed as dist
@@ -403,6 +468,7 @@ def run_b200_arm(a):
 
     # ---- CPU baseline on a bounded sample (rank 0, N=1 only) ----
     cpu = None
+    next_rows = None
     if world == 1 and not a.no_cpu_baseline:
         from oracle import bindings
         threads_all = host_threads()
@@ -425,6 +491,7 @@ def run_b200_arm(a):
             cpu["gpu_rows_with_identical_labels"] = round(float(same_rows.mean()), 6)
             cpu["gpu_counters_identical"] = bool(np.array_equal(res_cpu[3][lo:hi], first_counters[0]) and
                                                  np.array_equal(res_cpu[4][lo:hi], first_counters[1]))
+        next_rows = measure_next_rows(a, index, ref, queries[W * B:(W + 1) * B], k, threads_all)
         del ref
 
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -470,6 +537,8 @@ def run_b200_arm(a):
                      "formula": "sum_q D_q*bytes_per_vector + H_q*(4+4*M0), D/H = the reference's computed_distances/visited_members"},
         "cpu_baseline": cpu,
     }
+    if next_rows:
+        line["next_rows"] = next_rows
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
