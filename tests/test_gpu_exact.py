@@ -23,6 +23,8 @@ INDEX_CASES = [
     ("sorensen", "b1", 3000, 256, 10, 64, 0),
     ("l2sq", "f32", 1500, 2048, 10, 40, 30),     # 8 KB vectors: the tiled stage does not fit, one-query-per-warp scan kernel
     ("cos", "f32", 20000, 64, 10, 300, 0),       # many tiles per segment, several query groups
+    ("l2sq", "i8", 20000, 200, 10, 300, 50),     # IMMA path: 3 query tiles, ragged K slice, removed members
+    ("cos", "i8", 9000, 768, 40, 130, 0),        # IMMA path: k > 32
 ]
 
 

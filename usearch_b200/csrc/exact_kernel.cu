@@ -36,6 +36,7 @@
 #include <type_traits>
 
 #include "device_index.h"
+#include "exact_args.h"
 #include "frozen_index.h"
 #include "metrics.cuh"
 #include "warp_primitives.cuh"
@@ -44,21 +45,6 @@ namespace usearch_b200 {
 
 constexpr int EXACT_WARPS = 8;
 
-struct exact_args_t {
-    uint8_t const* queries = nullptr; /* rows padded to vec_stride, index scalar kind */
-    uint64_t query_stride = 0;
-    uint32_t nq = 0, k = 0;
-    uint32_t segments = 1, segment_len = 0; /* dataset cut into `segments` runs of `segment_len` slots (multiple of VPP) */
-    float* part_d = nullptr;                /* [nq x segments x k] */
-    uint32_t* part_s = nullptr;
-    uint32_t* part_n = nullptr;             /* [nq x segments] */
-    uint64_t* out_keys = nullptr;           /* [nq x k] */
-    float* out_dists = nullptr;
-    uint32_t* out_counts = nullptr;
-    uint32_t stage_stride = 0, off_bars = 0, off_stage = 0;
-    uint32_t slots_as_keys = 0;             /* 1: report the slot number as the key (free-function mode) */
-    uint32_t off_queries = 0;               /* tiled kernel: queries region precedes the barriers */
-};
 
 template <class M, class = void> struct has_finish_sw : std::false_type {};
 template <class M> struct has_finish_sw<M, decltype((void)&M::finish_sw, void())> : std::true_type {};
@@ -188,36 +174,6 @@ template <class M> struct exact_tile_t {
     static constexpr int TV = (32 / M::LPV) * VT;   /* vectors per tile */
     static constexpr int QPC = TILED_WARPS * QT;    /* queries per CTA */
 };
-
-/* sorted insert into a k-best list in global memory under (distance asc, slot desc); whole warp, uniform arguments */
-__device__ __forceinline__ void top_insert_global_keyed(float volatile* ld, uint32_t volatile* ls, uint32_t& size, uint32_t k, float cd,
-                                                        uint32_t cs, int lane) {
-    uint32_t pos = 0;
-    for (uint32_t base = 0; base < size; base += 32) {
-        uint32_t const i = base + (uint32_t)lane;
-        bool before = false;
-        if (i < size) {
-            float const d = ld[i];
-            before = d < cd || (d == cd && ls[i] > cs);
-        }
-        pos += __popc(__ballot_sync(0xffffffffu, before));
-    }
-    if (pos >= k) return;
-    uint32_t const new_size = size < k ? size + 1 : k;
-    for (int hi = (int)new_size - 1; hi > (int)pos; hi -= 32) { /* old [pos, new_size-1) moves one to the right, tail first */
-        int const i = hi - lane;
-        bool const mv = i > (int)pos;
-        float d = 0.f;
-        uint32_t sl = 0;
-        if (mv) { d = ld[i - 1]; sl = ls[i - 1]; }
-        __syncwarp();
-        if (mv) { ld[i] = d; ls[i] = sl; }
-        __syncwarp();
-    }
-    if (lane == 0) { ld[pos] = cd; ls[pos] = cs; }
-    __syncwarp();
-    size = new_size;
-}
 
 template <class M, bool SWAP>
 __global__ void __launch_bounds__(TILED_WARPS * 32, 1) exact_tiled_kernel(__grid_constant__ device_index_t const ix,
@@ -443,22 +399,26 @@ char const* exact_search_device(device_index_t const& ix, int sm_count, void con
     size_t const tiled_smem = ((size_t)qpc_tiled * ix.vec_stride + 16 + 127) / 128 * 128 + 2 * (size_t)tile_vectors * a.stage_stride;
     static int const forced = [] {
         char const* v = std::getenv("USEARCH_B200_EXACT");
-        return !v ? 0 : (std::strcmp(v, "scan") == 0 ? 1 : (std::strcmp(v, "tiled") == 0 ? 2 : 0));
+        return !v ? 0 : (std::strcmp(v, "scan") == 0 ? 1 : (std::strcmp(v, "tiled") == 0 ? 2 : (std::strcmp(v, "imma") == 0 ? 3 : 0)));
     }();
-    bool const tiled = forced == 1 ? false : tiled_smem <= 227 * 1024;
+    /* i8: integer sums are order independent, the tensor cores give the reference's bits (exact_imma.cu) */
+    bool const imma = ix.scalar == SCALAR_I8 && (forced == 0 || forced == 3) &&
+                      (ix.metric == METRIC_IP || ix.metric == METRIC_L2SQ || ix.metric == METRIC_COS);
+    if (forced == 3 && !imma) return "The IMMA exact-search kernel serves i8 vectors only";
+    bool const tiled = !imma && (forced == 1 ? false : tiled_smem <= 227 * 1024);
     if (forced == 2 && !tiled) return "Vectors too long for the tiled exact-search stage";
-    int const vpp = tiled ? tile_vectors : 32 / lpv;       /* vectors per tile */
-    uint32_t const qpc = tiled ? (uint32_t)qpc_tiled : (uint32_t)EXACT_WARPS;
+    int const vpp = imma ? exact_imma_tile_vectors() : (tiled ? tile_vectors : 32 / lpv); /* vectors per tile */
+    uint32_t const qpc = imma ? (uint32_t)exact_imma_tile_queries() : (tiled ? (uint32_t)qpc_tiled : (uint32_t)EXACT_WARPS);
     uint32_t off = qpc * (uint32_t)ix.vec_stride;
     a.off_queries = 0;
     a.off_bars = off;
     off = (off + 16 + 127) / 128 * 128;
     a.off_stage = off;
-    size_t const smem = off + 2 * (size_t)vpp * a.stage_stride;
+    size_t const smem = imma ? exact_imma_smem_bytes() : off + 2 * (size_t)vpp * a.stage_stride;
     if (smem > 227 * 1024) return "Vectors too long for the exact-search stage";
     uint32_t const groups = (uint32_t)((nq + qpc - 1) / qpc);
     /* cut the dataset so that the grid fills whole waves of the resident CTAs (1 per SM tiled, ~3 per SM otherwise) */
-    uint32_t const resident = (uint32_t)sm_count * (tiled ? 1u : 3u);
+    uint32_t const resident = (uint32_t)sm_count * (imma ? 2u : (tiled ? 1u : 3u));
     uint32_t const max_segments = std::max<uint32_t>(1, std::min<uint32_t>((ix.n + 8 * (uint32_t)vpp - 1) / (8 * (uint32_t)vpp), 65535u));
     uint32_t segments = 1;
     {
@@ -479,17 +439,29 @@ char const* exact_search_device(device_index_t const& ix, int sm_count, void con
     a.segments = segments;
     a.segment_len = seg_len;
     size_t const rows = nq * segments;
-    size_t const need = rows * k * 8 + rows * 4 + 64;
+    size_t const lists = rows * k * 8 + rows * 4;
+    size_t const norms_at = (lists + 15) / 16 * 16;
+    size_t const need = norms_at + (imma ? (nq + (size_t)ix.n) * 4 : 0) + 64;
     if (char const* e = scratch.reserve(need)) return e;
     a.part_d = reinterpret_cast<float*>(scratch.ptr);
     a.part_s = reinterpret_cast<uint32_t*>(scratch.ptr + rows * k * 4);
     a.part_n = reinterpret_cast<uint32_t*>(scratch.ptr + rows * k * 8);
+    if (imma && ix.metric != METRIC_IP) {
+        int* qn = reinterpret_cast<int*>(scratch.ptr + norms_at);
+        int* vn = qn + nq;
+        if (exact_imma_self_dots(a.queries, query_stride, ix.chunks16, (uint32_t)nq, qn, stream) != cudaSuccess ||
+            exact_imma_self_dots(ix.vectors, ix.vec_stride, ix.chunks16, ix.n, vn, stream) != cudaSuccess)
+            return "CUDA failure: i8 norms launch";
+        a.query_norms = qn;
+        a.vector_norms = vn;
+    }
     a.out_keys = d_keys;
     a.out_dists = d_dists;
     a.out_counts = d_counts;
     dim3 const grid(groups, segments);
     cudaError_t e = cudaErrorInvalidValue;
-    switch (ix.scalar) {
+    if (imma) e = exact_imma_launch(ix, a, swap, grid, stream);
+    else switch (ix.scalar) {
     case SCALAR_F32:
         if (ix.metric == METRIC_L2SQ) e = exact_launch_any_t<l2sq_f32_t>(tiled, ix, a, swap, grid, smem, stream);
         else if (ix.metric == METRIC_IP) e = exact_launch_any_t<ip_f32_t>(tiled, ix, a, swap, grid, smem, stream);

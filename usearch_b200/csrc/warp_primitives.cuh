@@ -112,4 +112,34 @@ __device__ __forceinline__ void top_insert_reg_keyed(float (&td)[TOP_E], uint32_
     size += full ? 0u : 1u;
 }
 
+/* sorted insert into a k-best list in global memory under (distance asc, slot desc); whole warp, uniform arguments */
+__device__ __forceinline__ void top_insert_global_keyed(float volatile* ld, uint32_t volatile* ls, uint32_t& size, uint32_t k, float cd,
+                                                        uint32_t cs, int lane) {
+    uint32_t pos = 0;
+    for (uint32_t base = 0; base < size; base += 32) {
+        uint32_t const i = base + (uint32_t)lane;
+        bool before = false;
+        if (i < size) {
+            float const d = ld[i];
+            before = d < cd || (d == cd && ls[i] > cs);
+        }
+        pos += __popc(__ballot_sync(0xffffffffu, before));
+    }
+    if (pos >= k) return;
+    uint32_t const new_size = size < k ? size + 1 : k;
+    for (int hi = (int)new_size - 1; hi > (int)pos; hi -= 32) { /* old [pos, new_size-1) moves one to the right, tail first */
+        int const i = hi - lane;
+        bool const mv = i > (int)pos;
+        float d = 0.f;
+        uint32_t sl = 0;
+        if (mv) { d = ld[i - 1]; sl = ls[i - 1]; }
+        __syncwarp();
+        if (mv) { ld[i] = d; ls[i] = sl; }
+        __syncwarp();
+    }
+    if (lane == 0) { ld[pos] = cd; ls[pos] = cs; }
+    __syncwarp();
+    size = new_size;
+}
+
 } // namespace usearch_b200
