@@ -211,19 +211,27 @@ __global__ void __launch_bounds__(IM_THREADS, 2) exact_imma_kernel(__grid_consta
             uint32_t size = rsize[row];
             float worst = rworst[row];
             size_t const list = ((size_t)qi * a.segments + blockIdx.y) * a.k;
+            /* lane l looks at columns 4l..4l+3 in one LDS.128; in the common case nothing passes and one ballot
+             * settles the whole row */
+            float4 const d4 = *reinterpret_cast<float4 const*>(dist + row * IM_DIST_STRIDE + lane * 4);
+            uint32_t const usable4 = (vmask[lane >> 3] >> ((lane & 7) * 4)) & 0xFu;
+            float const dv[4] = {d4.x, d4.y, d4.z, d4.w};
+            uint32_t pass = 0;
 #pragma unroll
-            for (int cb = 0; cb < 4; ++cb) {
-                float const d = dist[row * IM_DIST_STRIDE + cb * 32 + lane];
-                bool const usable = (vmask[cb] >> lane) & 1u;
-                uint32_t todo = __ballot_sync(0xffffffffu, usable && (size < a.k || !(d > worst)));
-                while (todo) {
-                    int const src_lane = __ffs(todo) - 1;
-                    todo &= todo - 1;
-                    float const cd = __shfl_sync(0xffffffffu, d, src_lane);
-                    uint32_t const cs = tile_base + (uint32_t)(cb * 32 + src_lane);
-                    if (size < a.k || !(cd > worst)) {
-                        top_insert_global_keyed(a.part_d + list, a.part_s + list, size, a.k, cd, cs, lane);
-                        if (size == a.k) worst = reinterpret_cast<float volatile*>(a.part_d)[list + a.k - 1];
+            for (int c = 0; c < 4; ++c) pass |= (((usable4 >> c) & 1u) && (size < a.k || !(dv[c] > worst))) ? (1u << c) : 0u;
+            if (__ballot_sync(0xffffffffu, pass != 0)) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t todo = __ballot_sync(0xffffffffu, (pass >> c) & 1u);
+                    while (todo) {
+                        int const src_lane = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        float const cd = __shfl_sync(0xffffffffu, dv[c], src_lane);
+                        uint32_t const cs = tile_base + (uint32_t)(src_lane * 4 + c);
+                        if (size < a.k || !(cd > worst)) {
+                            top_insert_global_keyed(a.part_d + list, a.part_s + list, size, a.k, cd, cs, lane);
+                            if (size == a.k) worst = reinterpret_cast<float volatile*>(a.part_d)[list + a.k - 1];
+                        }
                     }
                 }
             }
