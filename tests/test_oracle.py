@@ -12,7 +12,7 @@ import common
 from oracle import bindings
 from usearch_b200 import v2format
 
-FIXTURES = sorted(glob.glob(os.path.join(common.GOLDEN, "*.npz")))
+FIXTURES = sorted(glob.glob(os.path.join(common.GOLDEN, "*_n*.npz")))
 
 
 def ulp_distance(a: np.ndarray, b: np.ndarray) -> np.ndarray:
@@ -171,3 +171,20 @@ def test_port_cluster_matches_live_reference(metric, scalar, n, d, m):
     # level 0 and level 1 are the same stop; beyond the top level the entry point is the answer
     assert np.array_equal(ref.cluster(q, 0)[0], ref.cluster(q, 1)[0])
     assert len(set(ref.cluster(q, ref.max_level + 3)[0].tolist())) == 1
+
+
+@pytest.mark.parametrize("path", FIXTURES, ids=[os.path.basename(p)[:-4] for p in FIXTURES])
+def test_port_next_rows_match_golden(path):
+    """Exact search and cluster of the plain-C port against what the reference returned for the fixture graphs
+    (tests/golden/next_rows.npz, made by make_golden_next_rows.py)."""
+    name = os.path.basename(path)[:-4]
+    g, nr = np.load(path), np.load(os.path.join(common.GOLDEN, "next_rows.npz"))
+    port = bindings.PortIndex(g["blob"], int(g["ef"]))
+    keys, dist, counts = port.search(g["queries"], int(g["k"]), threads=2, exact=True)[:3]
+    assert np.array_equal(keys, nr[f"{name}/exact_keys"]) and np.array_equal(counts, nr[f"{name}/exact_counts"])
+    assert np.array_equal(dist.view(np.uint32), nr[f"{name}/exact_distances"].view(np.uint32))
+    for i, level in enumerate(nr[f"{name}/cluster_levels"]):
+        ck, cd, cc, cv = port.cluster(g["queries"], int(level))
+        assert np.array_equal(ck, nr[f"{name}/cluster_keys"][i]), f"level {level}"
+        assert np.array_equal(cd.view(np.uint32), nr[f"{name}/cluster_distances"][i].view(np.uint32))
+        assert np.array_equal(cc, nr[f"{name}/cluster_computed"][i]) and np.array_equal(cv, nr[f"{name}/cluster_visited"][i])
