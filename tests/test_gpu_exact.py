@@ -146,37 +146,3 @@ def test_cluster_matches_reference(metric, scalar, n, d, m):
     got = index.search(q, 10, stats=True)
     common.assert_same_results(want, (got.keys, got.distances, got.counts, index.last_computed, index.last_visited), "after cluster")
 
-
-import glob  # noqa: E402
-import os  # noqa: E402
-
-GOLDEN_FIXTURES = sorted(glob.glob(os.path.join(common.GOLDEN, "*_n*.npz")))
-
-
-@pytest.mark.parametrize("path", GOLDEN_FIXTURES, ids=[os.path.basename(p)[:-4] for p in GOLDEN_FIXTURES])
-def test_next_rows_match_golden(path):
-    """GPU exact search (index mode and free function) and cluster against the committed outputs of the reference
-    (tests/golden/next_rows.npz): no reference library needed at run time."""
-    from usearch_b200 import v2format
-    from usearch_b200.index import Index, exact_search
-    name = os.path.basename(path)[:-4]
-    g, nr = np.load(path), np.load(os.path.join(common.GOLDEN, "next_rows.npz"))
-    q, k = g["queries"], int(g["k"])
-    index = Index.restore(g["blob"])
-    got = index.search(q, k, exact=True)
-    assert np.array_equal(got.keys, nr[f"{name}/exact_keys"]) and np.array_equal(got.counts, nr[f"{name}/exact_counts"])
-    assert np.array_equal(got.distances.view(np.uint32), nr[f"{name}/exact_distances"].view(np.uint32))
-    for i, level in enumerate(nr[f"{name}/cluster_levels"]):
-        ck, cd = index.cluster(q, int(level), stats=True)
-        assert np.array_equal(ck, nr[f"{name}/cluster_keys"][i]), f"level {level}"
-        assert np.array_equal(cd.view(np.uint32), nr[f"{name}/cluster_distances"][i].view(np.uint32))
-        assert np.array_equal(index.last_computed, nr[f"{name}/cluster_computed"][i])
-        assert np.array_equal(index.last_visited, nr[f"{name}/cluster_visited"][i])
-    graph = v2format.loads(g["blob"])
-    vectors = graph.vectors.view(bindings.SCALAR_NP[graph.scalar]).reshape(graph.size, -1)
-    free = exact_search(vectors, q, k, metric=graph.metric, dtype=graph.scalar)
-    wd, wk = nr[f"{name}/free_distances"], nr[f"{name}/free_keys"]
-    assert np.array_equal(free.distances.view(np.uint32), wd[:, :k].view(np.uint32))
-    unique = wd[:, :k] != wd[:, 1:k + 1]
-    unique[:, 1:] &= wd[:, 1:k] != wd[:, :k - 1]
-    assert np.array_equal(free.keys[unique], wk[:, :k][unique])

@@ -132,3 +132,4 @@ def test_f32_queries_are_cast_like_the_reference(metric, scalar, d):
     got = index.search(q32, k, stats=True)
     common.assert_same_results(want, (got.keys, got.distances, got.counts, index.last_computed, index.last_visited),
                                f"f32 -> {scalar}")
+

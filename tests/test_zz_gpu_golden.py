@@ -1,0 +1,61 @@
+"""GPU parity against the COMMITTED golden vectors (tests/golden/*.npz: outputs of the unmodified reference, made by
+make_golden.py / make_golden_next_rows.py): nothing of the reference or the oracle is involved at run time.
+Collected last (file name) so that every other GPU test has reported before these start."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import common
+from oracle import bindings
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN_FIXTURES = sorted(glob.glob(os.path.join(common.GOLDEN, "*_n*.npz")))
+IDS = [os.path.basename(p)[:-4] for p in GOLDEN_FIXTURES]
+
+
+@pytest.mark.parametrize("path", GOLDEN_FIXTURES, ids=IDS)
+def test_search_matches_golden(path):
+    """Labels, distance bits, counts and both counters of the graph search."""
+    from usearch_b200.index import Index
+    g = np.load(path)
+    index = Index.restore(g["blob"])
+    index.expansion_search = int(g["ef"])
+    got = index.search(g["queries"], int(g["k"]), stats=True)
+    want = (g["keys_pinned"], g["distances_pinned"], g["counts_pinned"], g["computed_pinned"], g["visited_pinned"])
+    common.assert_same_results(want, (got.keys, got.distances, got.counts, index.last_computed, index.last_visited), "gpu vs golden")
+    # the reference's native SimSIMD dispatch on the generating host: same labels
+    assert np.array_equal(got.keys, g["keys_native"])
+
+
+# Written after the round's GPU budget was spent: the one attempt to run it ended in the job's time limit before this
+# test reported (cause not established - see DESIGN.md §8 "open items"), so it stays opt-in until it has been seen green.
+@pytest.mark.skipif(os.environ.get("USEARCH_B200_GOLDEN_NEXT_ROWS") != "1", reason="opt-in: USEARCH_B200_GOLDEN_NEXT_ROWS=1")
+@pytest.mark.parametrize("path", GOLDEN_FIXTURES, ids=IDS)
+def test_next_rows_match_golden(path):
+    """Exact search (index mode and free function) and cluster against tests/golden/next_rows.npz."""
+    from usearch_b200 import v2format
+    from usearch_b200.index import Index, exact_search
+    name = os.path.basename(path)[:-4]
+    g, nr = np.load(path), np.load(os.path.join(common.GOLDEN, "next_rows.npz"))
+    q, k = g["queries"], int(g["k"])
+    index = Index.restore(g["blob"])
+    got = index.search(q, k, exact=True)
+    assert np.array_equal(got.keys, nr[f"{name}/exact_keys"]) and np.array_equal(got.counts, nr[f"{name}/exact_counts"])
+    assert np.array_equal(got.distances.view(np.uint32), nr[f"{name}/exact_distances"].view(np.uint32))
+    for i, level in enumerate(nr[f"{name}/cluster_levels"]):
+        ck, cd = index.cluster(q, int(level), stats=True)
+        assert np.array_equal(ck, nr[f"{name}/cluster_keys"][i]), f"level {level}"
+        assert np.array_equal(cd.view(np.uint32), nr[f"{name}/cluster_distances"][i].view(np.uint32))
+        assert np.array_equal(index.last_computed, nr[f"{name}/cluster_computed"][i])
+        assert np.array_equal(index.last_visited, nr[f"{name}/cluster_visited"][i])
+    graph = v2format.loads(g["blob"])
+    vectors = graph.vectors.view(bindings.SCALAR_NP[graph.scalar]).reshape(graph.size, -1)
+    free = exact_search(vectors, q, k, metric=graph.metric, dtype=graph.scalar)
+    wd, wk = nr[f"{name}/free_distances"], nr[f"{name}/free_keys"]
+    assert np.array_equal(free.distances.view(np.uint32), wd[:, :k].view(np.uint32))
+    unique = wd[:, :k] != wd[:, 1:k + 1]
+    unique[:, 1:] &= wd[:, 1:k] != wd[:, :k - 1]
+    assert np.array_equal(free.keys[unique], wk[:, :k][unique])
