@@ -133,3 +133,4 @@ def test_f32_queries_are_cast_like_the_reference(metric, scalar, d):
     common.assert_same_results(want, (got.keys, got.distances, got.counts, index.last_computed, index.last_visited),
                                f"f32 -> {scalar}")
 
+

@@ -50,3 +50,13 @@ def test_native_clients_run(tmp_path):
     for binary, marker in ((c_bin, "C_ABI_OK"), (cpp_bin, "CPP_MIRROR_OK")):
         out = subprocess.run([binary, index_path, cases], capture_output=True, text=True, timeout=300)
         assert out.returncode == 0 and marker in out.stdout, out.stdout + out.stderr
+
+
+def test_half_words_summation_order(tmp_path):
+    """Host emulation of the 4-lane, by-accumulator split of the f16/bf16 metrics (metrics.cuh *_halfw_t): the bits
+    of the pinned oracle for l2sq / ip / cos."""
+    exe = tmp_path / "half_words"
+    subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-std=c99", "-I", os.path.join(common.ROOT, "oracle"),
+                    os.path.join(common.ROOT, "tests", "native", "test_half_words_order.c"), "-o", str(exe), "-lm"], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    assert "HALF_WORDS_ORDER_OK" in out

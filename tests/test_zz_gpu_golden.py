@@ -59,3 +59,34 @@ def test_next_rows_match_golden(path):
     unique = wd[:, :k] != wd[:, 1:k + 1]
     unique[:, 1:] &= wd[:, 1:k] != wd[:, :k - 1]
     assert np.array_equal(free.keys[unique], wk[:, :k][unique])
+
+
+@pytest.mark.parametrize("metric,scalar,n,d,m,ef,k,nq", [
+    ("cos", "f16", 6000, 768, 32, 128, 10, 128),
+    ("l2sq", "f16", 4000, 200, 16, 64, 10, 128),     # 400-byte vectors: ragged last chunk group
+    ("ip", "bf16", 4000, 256, 16, 64, 10, 128),
+    ("cos", "bf16", 3000, 136, 16, 300, 20, 64),     # ef > 256: shared-memory `top`
+])
+@pytest.mark.skipif(os.environ.get("USEARCH_B200_TEST_EXPERIMENTAL") != "1",
+                    reason="opt-in (USEARCH_B200_TEST_EXPERIMENTAL=1): the WORD variant has not run on hardware yet")
+def test_half_words_variant_matches_reference(metric, scalar, n, d, m, ef, k, nq):
+    """USEARCH_B200_HALF_WORDS=1: f16/bf16 with 4 lanes per vector split by accumulator (metrics.cuh *_halfw_t). The
+    switch is read once per process, hence the subprocess."""
+    import subprocess
+    import sys
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import numpy as np, common\n"
+        "from oracle import bindings\n"
+        "from usearch_b200.index import Index\n"
+        "base, q = common.make_collection(%d, %d, %r, %d)\n"
+        "ref, blob = common.build_reference_blob(base, %r, %r, %d, %d, threads=16)\n"
+        "want = bindings.PortIndex(blob, %d).search(q, %d, threads=16)\n"
+        "index = Index.restore(blob); index.expansion_search = %d\n"
+        "got = index.search(q, %d, stats=True)\n"
+        "common.assert_same_results(want, (got.keys, got.distances, got.counts, index.last_computed, index.last_visited), 'half words')\n"
+        "print('HALF_WORDS_OK')\n"
+    ) % (common.ROOT, os.path.join(common.ROOT, "tests"), n, d, scalar, nq, metric, scalar, d, m, ef, k, ef, k)
+    env = dict(os.environ, USEARCH_B200_HALF_WORDS="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "HALF_WORDS_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]

@@ -407,13 +407,13 @@ char const* frozen_index_t::plan(uint32_t k, uint32_t visited_cap_override, laun
          * (9.90 ms vs 9.79 ms per 4096-query batch): the kernel is limited by shared-memory traffic per vector,
          * not by thread-level parallelism, so whole-vector slots stay the default. The split point is a multiple
          * of 4*LPV chunks so that both halves run the unrolled loop. */
-        bool const can_split = lpv == 4 && d.chunks16 >= 64;
+        bool const can_split = lpv == 4 && search_stage_pad(d) == 64 && d.chunks16 >= 64;
         uint32_t segs = 1u;
         if (forced_segs == 2 && can_split) segs = 2u;
         pl.stage_segments = segs;
         pl.stage_seg_chunks = segs == 1 ? d.chunks16 : round_up((d.chunks16 + 1) / 2, 4 * lpv);
         /* slot stride = 16*LPV mod 128 bytes: the lanes of a quarter-warp then read disjoint banks */
-        pl.stage_stride = round_up(pl.stage_seg_chunks * 16, 128) + 16u * lpv;
+        pl.stage_stride = round_up(pl.stage_seg_chunks * 16, 128) + search_stage_pad(d);
         /* double-buffer the slots when at least 4 warps per SM still fit */
         size_t const two = off + 2 * (size_t)slots * pl.stage_stride + min_heap + cta_tax;
         pl.stage_sets = (forced_sets == 1 || forced_sets == 2) ? (uint32_t)forced_sets : (smem_sm / two >= 4 ? 2u : 1u);

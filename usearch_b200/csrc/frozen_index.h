@@ -25,6 +25,7 @@ int search_warps_per_block();
 bool search_is_staged(device_index_t const& ix);
 int search_stage_slots(device_index_t const& ix);
 int search_lanes_per_vector(device_index_t const& ix);
+uint32_t search_stage_pad(device_index_t const& ix);
 bool search_needs_norms(uint32_t metric, uint32_t scalar);
 cudaError_t search_compute_norms(device_index_t const& ix, float* norms, cudaStream_t stream);
 cudaError_t search_build_allow_bits(device_index_t const& ix, uint64_t const* allowed_sorted, uint32_t m, uint32_t* bits,

@@ -294,6 +294,96 @@ template <class C> struct cos_half_t {
     }
 };
 
+/*
+ *  WORD variants of the half-precision metrics (lane group of 4, STAGED kernel only).
+ *
+ *  The reference keeps 8 f32 accumulators; a 16-byte chunk holds exactly one element of each, so accumulator i sees
+ *  elements i, i+8, i+16, ... in order. Splitting the work over lanes BY ACCUMULATOR keeps every fma chain intact:
+ *  lane s of the group owns accumulators 2s and 2s+1 and reads the 32-bit word s of every chunk (unit = one word,
+ *  4 units per chunk). The f64 tree of reduce8_f64, ((v0+v4)+(v2+v6)) + ((v1+v5)+(v3+v7)), becomes an xor-2 shuffle
+ *  (v_i + v_{i+4}) followed by an xor-1 shuffle ((..)+(..)); f64 addition is commutative, so the lanes that see the
+ *  operands swapped produce the same bits. Compared with one lane per vector this gives 8 vectors per pass in two
+ *  double-buffered sets (like f32) instead of 32 in one, and a quarter of the shared memory per warp.
+ */
+__device__ __forceinline__ float reduce_words_f64(float const v[2]) {
+    double a = (double)v[0], b = (double)v[1];
+    a = __dadd_rn(a, __shfl_xor_sync(0xffffffffu, a, 2)); /* lanes 0,2: v0+v4 | lanes 1,3: v2+v6 */
+    b = __dadd_rn(b, __shfl_xor_sync(0xffffffffu, b, 2)); /* lanes 0,2: v1+v5 | lanes 1,3: v3+v7 */
+    a = __dadd_rn(a, __shfl_xor_sync(0xffffffffu, a, 1)); /* (v0+v4)+(v2+v6) */
+    b = __dadd_rn(b, __shfl_xor_sync(0xffffffffu, b, 1)); /* (v1+v5)+(v3+v7) */
+    return __double2float_rn(__dadd_rn(a, b));
+}
+
+template <class C> struct l2sq_halfw_t {
+    static constexpr int LPV = 4, UPC = 4;
+    static constexpr bool NORMS = false;
+    using unit_t = uint32_t;
+    template <class Q> static __device__ __forceinline__ float finalize(float raw, Q, float) { return raw; }
+    struct acc_t { float v[2]; };
+    struct qconst_t {};
+    static __device__ __forceinline__ void init(acc_t& a) { a.v[0] = a.v[1] = 0.f; }
+    static __device__ __forceinline__ void step(acc_t& a, uint32_t b, uint32_t q) {
+        float b0, b1, q0, q1;
+        C::widen(b, b0, b1);
+        C::widen(q, q0, q1);
+        float x0 = __fsub_rn(q0, b0), x1 = __fsub_rn(q1, b1);
+        a.v[0] = __fmaf_rn(x0, x0, a.v[0]);
+        a.v[1] = __fmaf_rn(x1, x1, a.v[1]);
+    }
+    static __device__ __forceinline__ float finish(acc_t const& a, qconst_t) { return reduce_words_f64(a.v); }
+    static __device__ __forceinline__ qconst_t prepare(uint4 const*, uint32_t, int) { return {}; }
+};
+
+template <class C> struct ip_halfw_t {
+    static constexpr int LPV = 4, UPC = 4;
+    static constexpr bool NORMS = false;
+    using unit_t = uint32_t;
+    template <class Q> static __device__ __forceinline__ float finalize(float raw, Q, float) { return raw; }
+    struct acc_t { float v[2]; };
+    struct qconst_t {};
+    static __device__ __forceinline__ void init(acc_t& a) { a.v[0] = a.v[1] = 0.f; }
+    static __device__ __forceinline__ void step(acc_t& a, uint32_t b, uint32_t q) {
+        float b0, b1, q0, q1;
+        C::widen(b, b0, b1);
+        C::widen(q, q0, q1);
+        a.v[0] = __fmaf_rn(q0, b0, a.v[0]);
+        a.v[1] = __fmaf_rn(q1, b1, a.v[1]);
+    }
+    static __device__ __forceinline__ float finish(acc_t const& a, qconst_t) { return __fsub_rn(1.0f, reduce_words_f64(a.v)); }
+    static __device__ __forceinline__ qconst_t prepare(uint4 const*, uint32_t, int) { return {}; }
+};
+
+template <class C> struct cos_halfw_t {
+    static constexpr int LPV = 4, UPC = 4;
+    static constexpr bool NORMS = true;
+    using unit_t = uint32_t;
+    struct acc_t { float v[2]; };
+    using qconst_t = typename cos_half_t<C>::qconst_t;
+    static __device__ __forceinline__ void init(acc_t& a) { a.v[0] = a.v[1] = 0.f; }
+    static __device__ __forceinline__ void step(acc_t& a, uint32_t b, uint32_t q) {
+        float b0, b1, q0, q1;
+        C::widen(b, b0, b1);
+        C::widen(q, q0, q1);
+        a.v[0] = __fmaf_rn(q0, b0, a.v[0]);
+        a.v[1] = __fmaf_rn(q1, b1, a.v[1]);
+    }
+    static __device__ __forceinline__ float finish(acc_t const& a, qconst_t) { return reduce_words_f64(a.v); }
+    static __device__ __forceinline__ float finalize(float ab, qconst_t qc, float b2) { return cos_normalize_f32(ab, qc.a2, b2); }
+    static __device__ __forceinline__ qconst_t prepare(uint4 const* q4, uint32_t chunks16, int lane) {
+        return cos_half_t<C>::prepare(q4, chunks16, lane); /* the query's own norm: same chain as the stored norms */
+    }
+};
+
+/* the unit a lane reads per step: a 16-byte chunk, or one 32-bit word of it (the WORD variants above) */
+template <class M, class = void> struct unit_of {
+    using type = uint4;
+    static constexpr uint32_t UPC = 1;
+};
+template <class M> struct unit_of<M, decltype((void)sizeof(typename M::unit_t), void())> {
+    using type = typename M::unit_t;
+    static constexpr uint32_t UPC = (uint32_t)M::UPC;
+};
+
 /* ---- i8 --------------------------------------------------------------------------------- */
 
 template <int LPV_> struct ip_i8_t {

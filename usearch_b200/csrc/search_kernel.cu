@@ -29,6 +29,8 @@
  */
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "device_index.h"
 #include "metrics.cuh"
 #include "warp_primitives.cuh"
@@ -320,8 +322,13 @@ __device__ __forceinline__ void measure_staged(device_index_t const& ix, search_
         uint32_t const pass = sp / segs, h = sp - pass * segs;
         uint32_t const base = pass * VPP, cnt = min((uint32_t)VPP, ncand - base), set = sp % nsets;
         uint32_t const c0 = h * seg_chunks, c1 = min(chunks, c0 + seg_chunks);
-        /* chunk j of the vector sits at slot offset (j - c0) * 16 */
-        uint4 const* buf = reinterpret_cast<uint4 const*>(w.stage + (size_t)(set * VPP + g) * a.stage_stride) - c0;
+        /* unit j of the vector (a 16-byte chunk, or a 32-bit word for the WORD metrics) sits at slot offset
+         * (j - c0 * UPC) * sizeof(unit) */
+        using U = typename unit_of<M>::type;
+        constexpr uint32_t UPC = unit_of<M>::UPC;
+        uint32_t const u0 = c0 * UPC, u1 = c1 * UPC;
+        U const* buf = reinterpret_cast<U const*>(w.stage + (size_t)(set * VPP + g) * a.stage_stride) - u0;
+        U const* qu = reinterpret_cast<U const*>(w.q4);
         bool const act = (uint32_t)g < cnt;
         if (h == 0) M::init(acc);
         if (a.phase_cycles) { /* introspection only: attribute the wait for the slowest slot to `vector_wait` */
@@ -333,14 +340,14 @@ __device__ __forceinline__ void measure_staged(device_index_t const& ix, search_
         if (act) {
             if (!a.phase_cycles) mbar_wait(w.bars_addr + 8u * set, (w.phase >> set) & 1u);
             /* 4 steps per iteration, the next iteration's 8 shared-memory loads issued before this one's math */
-            uint32_t j = c0 + sub;
-            if (j + 3 * LPV < c1) {
-                uint4 b0 = buf[j], b1 = buf[j + LPV], b2 = buf[j + 2 * LPV], b3 = buf[j + 3 * LPV];
-                uint4 q0 = w.q4[j], q1 = w.q4[j + LPV], q2 = w.q4[j + 2 * LPV], q3 = w.q4[j + 3 * LPV];
+            uint32_t j = u0 + sub;
+            if (j + 3 * LPV < u1) {
+                U b0 = buf[j], b1 = buf[j + LPV], b2 = buf[j + 2 * LPV], b3 = buf[j + 3 * LPV];
+                U q0 = qu[j], q1 = qu[j + LPV], q2 = qu[j + 2 * LPV], q3 = qu[j + 3 * LPV];
                 j += 4 * LPV;
-                for (; j + 3 * LPV < c1; j += 4 * LPV) {
-                    uint4 nb0 = buf[j], nb1 = buf[j + LPV], nb2 = buf[j + 2 * LPV], nb3 = buf[j + 3 * LPV];
-                    uint4 nq0 = w.q4[j], nq1 = w.q4[j + LPV], nq2 = w.q4[j + 2 * LPV], nq3 = w.q4[j + 3 * LPV];
+                for (; j + 3 * LPV < u1; j += 4 * LPV) {
+                    U nb0 = buf[j], nb1 = buf[j + LPV], nb2 = buf[j + 2 * LPV], nb3 = buf[j + 3 * LPV];
+                    U nq0 = qu[j], nq1 = qu[j + LPV], nq2 = qu[j + 2 * LPV], nq3 = qu[j + 3 * LPV];
                     M::step(acc, b0, q0);
                     M::step(acc, b1, q1);
                     M::step(acc, b2, q2);
@@ -353,7 +360,7 @@ __device__ __forceinline__ void measure_staged(device_index_t const& ix, search_
                 M::step(acc, b2, q2);
                 M::step(acc, b3, q3);
             }
-            for (; j < c1; j += LPV) M::step(acc, buf[j], w.q4[j]);
+            for (; j < u1; j += LPV) M::step(acc, buf[j], qu[j]);
         }
         if (h + 1 == segs) { /* last segment of the pass: horizontal reduce (warp-wide shuffles: every lane) */
             float d = M::finish(acc, qc);
@@ -844,6 +851,9 @@ template <class M, bool STAGED> static cudaError_t occupancy_t(int* blocks_per_s
 }
 
 #define DISPATCH_M(FN, M, ...) return staged ? FN<M, true>(__VA_ARGS__) : FN<M, false>(__VA_ARGS__)
+/* half precision: the WORD variant (4 lanes per vector, by accumulator) on the staged path when enabled */
+#define DISPATCH_H(FN, M, MW, ...) \
+    return staged ? (half_words_enabled() ? FN<MW, true>(__VA_ARGS__) : FN<M, true>(__VA_ARGS__)) : FN<M, false>(__VA_ARGS__)
 #define DISPATCH(FN, ...)                                                                                  \
     switch (ix.scalar) {                                                                                   \
     case SCALAR_F32:                                                                                       \
@@ -852,14 +862,14 @@ template <class M, bool STAGED> static cudaError_t occupancy_t(int* blocks_per_s
         if (ix.metric == METRIC_COS) DISPATCH_M(FN, cos_f32_t, __VA_ARGS__);                               \
         break;                                                                                             \
     case SCALAR_F16:                                                                                       \
-        if (ix.metric == METRIC_L2SQ) DISPATCH_M(FN, l2sq_half_t<f16_conv_t>, __VA_ARGS__);                \
-        if (ix.metric == METRIC_IP) DISPATCH_M(FN, ip_half_t<f16_conv_t>, __VA_ARGS__);                    \
-        if (ix.metric == METRIC_COS) DISPATCH_M(FN, cos_half_t<f16_conv_t>, __VA_ARGS__);                  \
+        if (ix.metric == METRIC_L2SQ) DISPATCH_H(FN, l2sq_half_t<f16_conv_t>, l2sq_halfw_t<f16_conv_t>, __VA_ARGS__);                \
+        if (ix.metric == METRIC_IP) DISPATCH_H(FN, ip_half_t<f16_conv_t>, ip_halfw_t<f16_conv_t>, __VA_ARGS__);                    \
+        if (ix.metric == METRIC_COS) DISPATCH_H(FN, cos_half_t<f16_conv_t>, cos_halfw_t<f16_conv_t>, __VA_ARGS__);                  \
         break;                                                                                             \
     case SCALAR_BF16:                                                                                      \
-        if (ix.metric == METRIC_L2SQ) DISPATCH_M(FN, l2sq_half_t<bf16_conv_t>, __VA_ARGS__);               \
-        if (ix.metric == METRIC_IP) DISPATCH_M(FN, ip_half_t<bf16_conv_t>, __VA_ARGS__);                   \
-        if (ix.metric == METRIC_COS) DISPATCH_M(FN, cos_half_t<bf16_conv_t>, __VA_ARGS__);                 \
+        if (ix.metric == METRIC_L2SQ) DISPATCH_H(FN, l2sq_half_t<bf16_conv_t>, l2sq_halfw_t<bf16_conv_t>, __VA_ARGS__);               \
+        if (ix.metric == METRIC_IP) DISPATCH_H(FN, ip_half_t<bf16_conv_t>, ip_halfw_t<bf16_conv_t>, __VA_ARGS__);                   \
+        if (ix.metric == METRIC_COS) DISPATCH_H(FN, cos_half_t<bf16_conv_t>, cos_halfw_t<bf16_conv_t>, __VA_ARGS__);                 \
         break;                                                                                             \
     case SCALAR_I8:                                                                                        \
         if (ix.metric == METRIC_L2SQ) DISPATCH_M(FN, l2sq_i8_t<4>, __VA_ARGS__);                           \
@@ -879,7 +889,21 @@ template <class M, bool STAGED> static cudaError_t occupancy_t(int* blocks_per_s
 constexpr uint32_t STAGED_MIN_BYTES = 256;
 
 bool search_is_staged(device_index_t const& ix) { return ix.scalar != SCALAR_B1 && ix.vec_stride >= STAGED_MIN_BYTES; }
-int search_lanes_per_vector(device_index_t const& ix) { return (ix.scalar == SCALAR_F16 || ix.scalar == SCALAR_BF16) ? 1 : 4; }
+/* EXPERIMENTAL (not yet validated on hardware, off by default): USEARCH_B200_HALF_WORDS=1 */
+bool half_words_enabled() {
+    static bool const on = [] { char const* v = std::getenv("USEARCH_B200_HALF_WORDS"); return v && std::atoi(v) == 1; }();
+    return on;
+}
+static bool is_half(device_index_t const& ix) { return ix.scalar == SCALAR_F16 || ix.scalar == SCALAR_BF16; }
+int search_lanes_per_vector(device_index_t const& ix) {
+    if (!is_half(ix)) return 4;
+    return search_is_staged(ix) && half_words_enabled() ? 4 : 1;
+}
+/* bytes added to a 128-byte-rounded slot so that the lane groups of a pass hit disjoint banks: 16*LPV for 16-byte
+ * units (each lane of a group reads its own chunk), 16 for word units (a group reads one chunk) */
+uint32_t search_stage_pad(device_index_t const& ix) {
+    return is_half(ix) && search_lanes_per_vector(ix) == 4 ? 16u : 16u * (uint32_t)search_lanes_per_vector(ix);
+}
 int search_stage_slots(device_index_t const& ix) { return search_is_staged(ix) ? 32 / search_lanes_per_vector(ix) : 0; }
 
 cudaError_t search_launch(device_index_t const& ix, search_args_t const& a, int blocks, size_t smem, cudaStream_t stream) {
