@@ -67,6 +67,10 @@ def parse_args():
     p.add_argument("--rank-latent", type=int, default=16)
     p.add_argument("--cpu-sample-seconds", type=float, default=12.0)
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--parallelism", default="shard", choices=["shard", "replica"],
+                   help="N > 1 only. shard (default, the north-star layout): the collection is split by key, every rank "
+                        "searches every query, one NCCL all-gather + merge. replica: every rank holds the whole index and "
+                        "serves its own batch, no exchange (SURVEY.md 8e: 'replicated index, split batch').")
     return p.parse_args()
 
 
@@ -91,8 +95,8 @@ def make_base(a, shard: int, shards: int) -> tuple[np.ndarray, np.ndarray]:
     return keys, datagen.to_scalar(full[shard::shards], a.dtype)
 
 
-def make_queries(a, total: int) -> np.ndarray:
-    return datagen.to_scalar(datagen.latent(total, a.dim, seed=43, rank=a.rank_latent), a.dtype)
+def make_queries(a, total: int, stream: int = 0) -> np.ndarray:
+    return datagen.to_scalar(datagen.latent(total, a.dim, seed=43 + 1000 * stream, rank=a.rank_latent), a.dtype)
 
 
 def get_index_blob(a, shard: int, shards: int, threads: int):
@@ -340,8 +344,15 @@ def run_b200_arm(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
 
-    threads = max(1, host_threads() // world)
-    keys, base, blob, path, info = get_index_blob(a, rank, world, threads)
+    # shard: rank r holds the keys congruent to r mod world; replica: every rank holds everything (rank 0 builds it)
+    shards = world if a.parallelism == "shard" else 1
+    shard_id = rank if shards > 1 else 0
+    threads = max(1, host_threads() // shards)
+    if shards == 1 and world > 1:
+        if rank == 0:
+            get_index_blob(a, 0, 1, threads)
+        dist.barrier()
+    keys, base, blob, path, info = get_index_blob(a, shard_id, shards, threads)
     t0 = time.time()
     index = Index.restore(path)
     index.expansion_search = a.ef
@@ -350,7 +361,7 @@ def run_b200_arm(a):
 
     B, k, W, K = a.batch, a.k, a.warmup, a.steps
     total = (W + K) * B
-    queries = make_queries(a, total)
+    queries = make_queries(a, total, stream=0 if shards > 1 or world == 1 else rank)  # replicas serve different batches
     bpv = queries.strides[0]
     vs = (bpv + 15) // 16 * 16
 
@@ -376,7 +387,7 @@ def run_b200_arm(a):
         qs = q_dev[s * B:(s + 1) * B]
         index.search_device(qs.data_ptr(), B, vs, k, keys_dev.data_ptr(), dist_dev.data_ptr(), cnt_dev.data_ptr(),
                             comp_dev.data_ptr(), vis_dev.data_ptr(), stream.cuda_stream)
-        if world > 1:
+        if shards > 1:
             return merge_topk()
         return keys_dev, dist_dev
 
@@ -434,7 +445,7 @@ def run_b200_arm(a):
     t0 = time.perf_counter()
     for s in range(W, W + K):
         res = index.search(q_host[s * B:(s + 1) * B], k)
-        if world > 1:
+        if shards > 1:
             keys_dev.copy_(torch.from_numpy(res.keys.view(np.int64)), non_blocking=False)
             dist_dev.copy_(torch.from_numpy(res.distances), non_blocking=False)
             cnt_dev.copy_(torch.from_numpy(res.counts.astype(np.int32)), non_blocking=False)
@@ -450,7 +461,7 @@ def run_b200_arm(a):
     # ---- quality gate: recall@10 against exact ground truth over the whole (sharded) collection ----
     q0 = queries[W * B:(W + 1) * B]
     gt_k, gt_d = exact_topk_gpu(base, keys, q0, a.metric, k, device)
-    if world > 1:
+    if shards > 1:
         gk = [torch.zeros_like(gt_k) for _ in range(world)]
         gd = [torch.zeros_like(gt_d) for _ in range(world)]
         dist.all_gather(gk, gt_k)
@@ -458,7 +469,7 @@ def run_b200_arm(a):
         sel = torch.topk(torch.cat(gd, 1), k, dim=1, largest=False).indices
         gt_k = torch.gather(torch.cat(gk, 1), 1, sel)
     found_k, found_c = first_found
-    counts = found_c.cpu().numpy() if world == 1 else np.full(B, k)
+    counts = found_c.cpu().numpy() if shards == 1 else np.full(B, k)
     recall = recall_at_k(found_k.cpu().numpy().astype(np.uint64), counts, gt_k.cpu().numpy().astype(np.uint64))
 
     if rank != 0:
@@ -515,10 +526,11 @@ def run_b200_arm(a):
     value = units / (elapsed_ms * 1e-3)
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": "queries/s", "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": round(elapsed_ms / K, 3), "higher_is_better": True, "scaling": "weak" if world == 1 else "strong",
+        "ms_per_step": round(elapsed_ms / K, 3), "higher_is_better": True, "scaling": "weak" if shards == 1 else "strong",
         "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
         "config": {
-            "workload": workload_name(a), "parallelism": "single GPU" if world == 1 else f"shard-by-key x{world} + NCCL all-gather top-k",
+            "workload": workload_name(a), "parallelism": "single GPU" if world == 1 else (f"shard-by-key x{world} + NCCL all-gather top-k" if shards > 1 else
+                                                                         f"{world} replicas of the whole index, one batch each, no exchange"),
             "l2_policy": "index (vectors+graph) larger than the 126 MB L2; every step uses a fresh query batch",
             "index_hbm_gb": round(index.memory_usage / 1e9, 3), "index_build": info,
             "computed_distances_per_query": round(d_per_q, 1), "visited_members_per_query": round(h_per_q, 1),
