@@ -745,8 +745,12 @@ __device__ __forceinline__ void search_one(device_index_t const& ix, search_args
 #undef PHASE
 }
 
-template <class M, bool STAGED>
-__global__ void __launch_bounds__(THREADS, STAGED ? 8 : 16) hnsw_search_kernel(__grid_constant__ device_index_t const ix,
+/* MIN_CTAS: resident CTAs per SM the register allocation must allow. 8 for the staged kernel, 16 for the direct one;
+ * EXPERIMENTAL (USEARCH_B200_STAGED_DENSE=1, not yet run on hardware): the staged kernel at 16 (<= 128 registers, no
+ * spills) for vectors of 1-1.5 KB - i8, f16/bf16 with the WORD metrics - where a hop moves few bytes and the fixed
+ * per-hop latency needs more warps to hide. */
+template <class M, bool STAGED, int MIN_CTAS = (STAGED ? 8 : 16)>
+__global__ void __launch_bounds__(THREADS, MIN_CTAS) hnsw_search_kernel(__grid_constant__ device_index_t const ix,
                                                               __grid_constant__ search_args_t const a) {
     extern __shared__ __align__(128) uint8_t smem[];
     int const lane = threadIdx.x;
@@ -850,6 +854,24 @@ template <class M, bool STAGED> static cudaError_t occupancy_t(int* blocks_per_s
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, hnsw_search_kernel<M, STAGED>, THREADS, smem);
 }
 
+bool half_words_enabled();
+
+template <class M> static cudaError_t launch_dense_t(device_index_t const& ix, search_args_t const& a, int blocks, size_t smem, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(hnsw_search_kernel<M, true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    hnsw_search_kernel<M, true, 16><<<blocks, THREADS, smem, stream>>>(ix, a);
+    return cudaGetLastError();
+}
+template <class M> static cudaError_t occupancy_dense_t(int* blocks_per_sm, size_t smem) {
+    cudaError_t e = cudaFuncSetAttribute(hnsw_search_kernel<M, true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, hnsw_search_kernel<M, true, 16>, THREADS, smem);
+}
+static bool staged_dense_enabled() {
+    static bool const on = [] { char const* v = std::getenv("USEARCH_B200_STAGED_DENSE"); return v && std::atoi(v) == 1; }();
+    return on;
+}
+
 #define DISPATCH_M(FN, M, ...) return staged ? FN<M, true>(__VA_ARGS__) : FN<M, false>(__VA_ARGS__)
 /* half precision: the WORD variant (4 lanes per vector, by accumulator) on the staged path when enabled */
 #define DISPATCH_H(FN, M, MW, ...) \
@@ -906,13 +928,32 @@ uint32_t search_stage_pad(device_index_t const& ix) {
 }
 int search_stage_slots(device_index_t const& ix) { return search_is_staged(ix) ? 32 / search_lanes_per_vector(ix) : 0; }
 
+#define DISPATCH_DENSE(FN, ...)                                                                             \
+    if (staged_dense_enabled() && search_is_staged(ix)) {                                                  \
+        if (ix.scalar == SCALAR_I8) {                                                                      \
+            if (ix.metric == METRIC_L2SQ) return FN<l2sq_i8_t<4>>(__VA_ARGS__);                            \
+            if (ix.metric == METRIC_IP) return FN<ip_i8_t<4>>(__VA_ARGS__);                                \
+            if (ix.metric == METRIC_COS) return FN<cos_i8_t<4>>(__VA_ARGS__);                              \
+        } else if (ix.scalar == SCALAR_F16 && half_words_enabled()) {                                      \
+            if (ix.metric == METRIC_L2SQ) return FN<l2sq_halfw_t<f16_conv_t>>(__VA_ARGS__);                \
+            if (ix.metric == METRIC_IP) return FN<ip_halfw_t<f16_conv_t>>(__VA_ARGS__);                    \
+            if (ix.metric == METRIC_COS) return FN<cos_halfw_t<f16_conv_t>>(__VA_ARGS__);                  \
+        } else if (ix.scalar == SCALAR_BF16 && half_words_enabled()) {                                     \
+            if (ix.metric == METRIC_L2SQ) return FN<l2sq_halfw_t<bf16_conv_t>>(__VA_ARGS__);               \
+            if (ix.metric == METRIC_IP) return FN<ip_halfw_t<bf16_conv_t>>(__VA_ARGS__);                   \
+            if (ix.metric == METRIC_COS) return FN<cos_halfw_t<bf16_conv_t>>(__VA_ARGS__);                 \
+        }                                                                                                  \
+    }
+
 cudaError_t search_launch(device_index_t const& ix, search_args_t const& a, int blocks, size_t smem, cudaStream_t stream) {
     bool const staged = search_is_staged(ix);
+    DISPATCH_DENSE(launch_dense_t, ix, a, blocks, smem, stream)
     DISPATCH(launch_t, ix, a, blocks, smem, stream)
 }
 
 cudaError_t search_occupancy(device_index_t const& ix, int* blocks_per_sm, size_t smem) {
     bool const staged = search_is_staged(ix);
+    DISPATCH_DENSE(occupancy_dense_t, blocks_per_sm, smem)
     DISPATCH(occupancy_t, blocks_per_sm, smem)
 }
 
