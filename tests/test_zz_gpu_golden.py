@@ -65,17 +65,22 @@ def test_next_rows_match_golden(path):
     assert np.array_equal(free.keys[unique], wk[:, :k][unique])
 
 
-@pytest.mark.parametrize("metric,scalar,n,d,m,ef,k,nq", [
-    ("cos", "f16", 6000, 768, 32, 128, 10, 128),
-    ("l2sq", "f16", 4000, 200, 16, 64, 10, 128),     # 400-byte vectors: ragged last chunk group
-    ("ip", "bf16", 4000, 256, 16, 64, 10, 128),
-    ("cos", "bf16", 3000, 136, 16, 300, 20, 64),     # ef > 256: shared-memory `top`
+@pytest.mark.parametrize("flags,metric,scalar,n,d,m,ef,k,nq", [
+    ("HALF_WORDS", "cos", "f16", 6000, 768, 32, 128, 10, 128),
+    ("HALF_WORDS", "l2sq", "f16", 4000, 200, 16, 64, 10, 128),     # 400-byte vectors: ragged last chunk group
+    ("HALF_WORDS", "ip", "bf16", 4000, 256, 16, 64, 10, 128),
+    ("HALF_WORDS", "cos", "bf16", 3000, 136, 16, 300, 20, 64),     # ef > 256: shared-memory `top`
+    ("STAGED_DENSE", "ip", "i8", 8000, 1024, 16, 128, 10, 256),    # 16 resident warps per SM
+    ("STAGED_DENSE", "cos", "i8", 4000, 256, 16, 64, 10, 128),
+    ("STAGED_DENSE,STAGE_SETS=1", "l2sq", "i8", 4000, 512, 16, 64, 10, 128),
+    ("HALF_WORDS,STAGED_DENSE", "cos", "f16", 6000, 768, 32, 256, 10, 128),
 ])
 @pytest.mark.skipif(os.environ.get("USEARCH_B200_TEST_EXPERIMENTAL") != "1",
-                    reason="opt-in (USEARCH_B200_TEST_EXPERIMENTAL=1): the WORD variant has not run on hardware yet")
-def test_half_words_variant_matches_reference(metric, scalar, n, d, m, ef, k, nq):
-    """USEARCH_B200_HALF_WORDS=1: f16/bf16 with 4 lanes per vector split by accumulator (metrics.cuh *_halfw_t). The
-    switch is read once per process, hence the subprocess."""
+                    reason="opt-in (USEARCH_B200_TEST_EXPERIMENTAL=1): these variants have not run on hardware yet")
+def test_experimental_variants_match_reference(flags, metric, scalar, n, d, m, ef, k, nq):
+    """The off-by-default kernel variants (USEARCH_B200_HALF_WORDS: f16/bf16 with 4 lanes per vector split by
+    accumulator; USEARCH_B200_STAGED_DENSE: 16 resident warps per SM) against the reference. The switches are read once
+    per process, hence the subprocess."""
     import subprocess
     import sys
     code = (
@@ -88,9 +93,12 @@ def test_half_words_variant_matches_reference(metric, scalar, n, d, m, ef, k, nq
         "want = bindings.PortIndex(blob, %d).search(q, %d, threads=16)\n"
         "index = Index.restore(blob); index.expansion_search = %d\n"
         "got = index.search(q, %d, stats=True)\n"
-        "common.assert_same_results(want, (got.keys, got.distances, got.counts, index.last_computed, index.last_visited), 'half words')\n"
-        "print('HALF_WORDS_OK')\n"
+        "common.assert_same_results(want, (got.keys, got.distances, got.counts, index.last_computed, index.last_visited), 'variant')\n"
+        "print('VARIANT_OK')\n"
     ) % (common.ROOT, os.path.join(common.ROOT, "tests"), n, d, scalar, nq, metric, scalar, d, m, ef, k, ef, k)
-    env = dict(os.environ, USEARCH_B200_HALF_WORDS="1")
+    env = dict(os.environ)
+    for flag in flags.split(","):
+        name, _, value = flag.partition("=")
+        env["USEARCH_B200_" + name] = value or "1"
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
-    assert out.returncode == 0 and "HALF_WORDS_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+    assert out.returncode == 0 and "VARIANT_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
