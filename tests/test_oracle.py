@@ -188,3 +188,38 @@ def test_port_next_rows_match_golden(path):
         assert np.array_equal(ck, nr[f"{name}/cluster_keys"][i]), f"level {level}"
         assert np.array_equal(cd.view(np.uint32), nr[f"{name}/cluster_distances"][i].view(np.uint32))
         assert np.array_equal(cc, nr[f"{name}/cluster_computed"][i]) and np.array_equal(cv, nr[f"{name}/cluster_visited"][i])
+
+
+@pytest.mark.skipif(not common.have_reference(), reason="oracle/_ref not built")
+def test_port_matches_live_reference_on_random_small_cases():
+    """Forty seeded random configurations at the small end (n from 1, k > n, ef < k, removed members, duplicate vectors,
+    every scalar kind): graph search, exact search and cluster of the port against the reference, bit for bit."""
+    rng = np.random.default_rng(2026)
+    kinds = [("l2sq", "f32"), ("cos", "f32"), ("ip", "f32"), ("cos", "f16"), ("l2sq", "bf16"), ("ip", "i8"), ("cos", "i8"),
+             ("hamming", "b1"), ("tanimoto", "b1"), ("sorensen", "b1")]
+    for case in range(40):
+        metric, scalar = kinds[case % len(kinds)]
+        n = int(rng.integers(1, 200))
+        d = int(rng.integers(1, 6)) * 8 if scalar == "b1" else int(rng.integers(1, 41))
+        m = int(rng.integers(2, 9))
+        ef = int(rng.integers(1, 40))
+        k = int(rng.integers(1, 25))
+        base, q = common.make_collection(n, d, scalar, 16, seed=100 + case, rank=min(4, d))
+        if n > 4:
+            base[n // 2] = base[0]                                  # a duplicate: equal distances
+        keys = rng.permutation(np.arange(10 * n, dtype=np.uint64))[:n]
+        ref, _ = common.build_reference_blob(base, metric, scalar, d, m, expansion_add=int(rng.integers(2, 40)), threads=1, keys=keys)
+        for key in keys[:int(rng.integers(0, max(1, n // 3)))]:
+            ref.remove(int(key))
+        blob = ref.save()
+        ref.pin_metric(True)
+        ref.change_expansion_search(ef)
+        port = bindings.PortIndex(blob, ef)
+        what = f"case {case}: {metric}/{scalar} n={n} d={d} M={m} ef={ef} k={k}"
+        common.assert_same_results(ref.search(q, k, threads=1), port.search(q, k, threads=2), what)
+        common.assert_same_results(ref.search(q, k, threads=1, exact=True)[:3], port.search(q, k, threads=2, exact=True)[:3], what + " exact")
+        if ref.size:
+            for level in (0, 1, ref.max_level + 1):
+                for a, b in zip(ref.cluster(q, level), port.cluster(q, level)):
+                    assert np.array_equal(a.view(np.uint32) if a.dtype == np.float32 else a,
+                                          b.view(np.uint32) if b.dtype == np.float32 else b), what + f" cluster {level}"
