@@ -100,7 +100,7 @@ size_t usearch_size(usearch_index_t index, usearch_error_t* error);          /* 
 size_t usearch_capacity(usearch_index_t index, usearch_error_t* error);      /* usearch.h:238 */
 size_t usearch_dimensions(usearch_index_t index, usearch_error_t* error);    /* usearch.h:245 */
 size_t usearch_connectivity(usearch_index_t index, usearch_error_t* error);  /* usearch.h:252 */
-void usearch_reserve(usearch_index_t index, size_t capacity, usearch_error_t* error); /* usearch.h:260; no-op on a frozen index */
+void usearch_reserve(usearch_index_t index, size_t capacity, usearch_error_t* error); /* usearch.h:260, c/lib.cpp:365-370: room for `capacity` members in HBM */
 size_t usearch_expansion_add(usearch_index_t index, usearch_error_t* error);          /* usearch.h:268 */
 size_t usearch_expansion_search(usearch_index_t index, usearch_error_t* error);       /* usearch.h:276 */
 void usearch_change_expansion_add(usearch_index_t index, size_t expansion, usearch_error_t* error);    /* usearch.h:284 */
@@ -135,8 +135,12 @@ size_t usearch_search_many(usearch_index_t index, void const* queries, size_t qu
                            usearch_distance_t* distances, size_t distances_stride,      //
                            size_t* counts, usearch_error_t* error);
 
-/* ---- exported so existing bindings link; a frozen index reports an error ------------------- */
+/* ---- mutation and lookups by key ---------------------------------------------------------------- */
 
+/* usearch.h:338, c/lib.cpp:378-386 -> index_gt::add (index.hpp:2780-2880). The member is linked into the graph on the GPU
+ * by the batched builder (csrc/builder.cu) — a batch of one here; usearch_b200_add_many below is the throughput entry.
+ * Capacity grows on demand (the reference's C layer reports "Reserve capacity ahead of insertions!" instead). Removed
+ * entries keep their slot (tombstone, skipped by searches); slots are not recycled. */
 void usearch_add(usearch_index_t index, usearch_key_t key, void const* vector, usearch_scalar_kind_t vector_kind, usearch_error_t* error); /* usearch.h:338 */
 bool usearch_contains(usearch_index_t index, usearch_key_t key, usearch_error_t* error);   /* usearch.h:349 */
 size_t usearch_count(usearch_index_t index, usearch_key_t key, usearch_error_t* error);    /* usearch.h:358 */
@@ -151,6 +155,17 @@ void usearch_exact_search(void const* dataset, size_t dataset_size, size_t datas
                           size_t keys_stride, usearch_distance_t* distances, size_t distances_stride,
                           usearch_error_t* error); /* usearch.h:467; runs on the GPU, `threads` ignored, count <= 256 */
 void usearch_clear(usearch_index_t index, usearch_error_t* error); /* usearch.h:481 */
+
+/* NEW (additive). GPU-assisted construction: `count` keys and vectors in one call. The vectors (any
+ * supported scalar kind, rows `vectors_stride` bytes apart, 0 = dense) are copied into HBM, cast on the device if needed, and
+ * linked batch by batch: one INSERT-mode launch of the search kernel per batch produces every member's candidates on every
+ * level (search_to_insert_, index.hpp:4010-4079), two more kernels select forward and reverse links with the reference's
+ * heuristic (refine_, index.hpp:4276-4318). Replaces the thread-pool loop of python/lib.cpp:171-258 (`add_typed_to_index`). */
+void usearch_b200_add_many(usearch_index_t index, usearch_key_t const* keys, void const* vectors, size_t count,
+                           size_t vectors_stride, usearch_scalar_kind_t vector_kind, usearch_error_t* error);
+/* The same with `keys` and `vectors` in DEVICE memory on the index's GPU. */
+void usearch_b200_add_many_device(usearch_index_t index, usearch_key_t const* keys, void const* vectors, size_t count,
+                                  size_t vectors_stride, usearch_scalar_kind_t vector_kind, usearch_error_t* error);
 
 /* ---- additive, device-resident variants ---------------------------------------------------- */
 

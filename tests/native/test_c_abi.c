@@ -20,6 +20,8 @@
         }                                                                     \
     } while (0)
 
+static int even_keys_only(usearch_key_t key, void* state) { (void)state; return key % 2 == 0; }
+
 int main(int argc, char** argv) {
     if (argc < 3) return 2;
     usearch_error_t error = NULL;
@@ -87,15 +89,6 @@ int main(int argc, char** argv) {
     /* count == 0 is an empty result, not an error (index.hpp:3025-3026) */
     EXPECT(usearch_search(index, queries, usearch_scalar_f32_k, 0, keys, dist, &error) == 0 && !error);
 
-    /* mutations report the frozen index through the error string and touch nothing */
-    usearch_add(index, 42, queries, usearch_scalar_f32_k, &error);
-    EXPECT(error && strstr(error, "frozen"));
-    error = NULL;
-    EXPECT(usearch_remove(index, 42, &error) == 0 && error);
-    error = NULL;
-    EXPECT(usearch_filtered_search(index, queries, usearch_scalar_f32_k, k, (int (*)(usearch_key_t, void*))1, NULL, keys, dist, &error) == 0 && error);
-    error = NULL;
-
     /* save -> load into a second handle -> identical answers (c/test.c save/load section) */
     size_t length = usearch_serialized_length(index, &error);
     void* buffer = malloc(length);
@@ -115,6 +108,48 @@ int main(int argc, char** argv) {
     EXPECT(error);
     error = NULL;
     usearch_free(broken, &error);
+
+    /* lookups by key (c/test.c "contains/count/get" sections) */
+    EXPECT(usearch_contains(index, want_keys[0], &error) && !error);
+    EXPECT(usearch_count(index, want_keys[0], &error) == 1 && !error);
+    EXPECT(!usearch_contains(index, 0xDEADBEEFull, &error) && !error);
+    float* stored = (float*)malloc(dims * 4);
+    EXPECT(usearch_get(index, want_keys[0], 1, stored, usearch_scalar_f32_k, &error) == 1 && !error);
+    EXPECT(usearch_get(index, 0xDEADBEEFull, 1, stored, usearch_scalar_f32_k, &error) == 0 && !error);
+    /* the closest match of query 0 is at the distance the index reports for that pair (usearch_distance) */
+    {
+        float d = usearch_distance(queries, stored, usearch_scalar_f32_k, dims, usearch_metric_cos_k, &error);
+        EXPECT(!error && memcmp(&d, want_dist, 4) == 0);
+    }
+
+    /* a host predicate (c/test.c test_filtered_search): only even keys may be returned */
+    {
+        size_t found = usearch_filtered_search(index, queries, usearch_scalar_f32_k, k, even_keys_only, NULL, keys, dist, &error);
+        EXPECT(!error && found > 0);
+        for (size_t i = 0; i < found; ++i) EXPECT(keys[i] % 2 == 0);
+    }
+
+    /* add -> found -> remove -> gone (c/test.c test_add_vector / test_remove_vector) */
+    {
+        size_t const before = usearch_size(index, &error);
+        usearch_key_t const fresh = 0x7000000000ull;
+        usearch_add(index, fresh, queries, usearch_scalar_f32_k, &error);
+        EXPECT(!error);
+        EXPECT(usearch_size(index, &error) == before + 1 && usearch_contains(index, fresh, &error));
+        size_t found = usearch_search(index, queries, usearch_scalar_f32_k, k, keys, dist, &error);
+        EXPECT(!error && found >= 1 && keys[0] == fresh);
+        usearch_add(index, fresh, queries, usearch_scalar_f32_k, &error); /* duplicates are refused (not a multi-index) */
+        EXPECT(error);
+        error = NULL;
+        EXPECT(usearch_rename(index, fresh, fresh + 1, &error) == 1 && !error && usearch_contains(index, fresh + 1, &error));
+        EXPECT(usearch_remove(index, fresh + 1, &error) == 1 && !error);
+        EXPECT(usearch_remove(index, fresh + 1, &error) == 0 && !error);
+        EXPECT(usearch_size(index, &error) == before && !usearch_contains(index, fresh + 1, &error));
+        found = usearch_search(index, queries, usearch_scalar_f32_k, k, keys, dist, &error);
+        EXPECT(!error);
+        for (size_t i = 0; i < found; ++i) EXPECT(keys[i] != fresh + 1 && keys[i] != fresh);
+    }
+    free(stored);
 
     usearch_clear(index, &error);
     EXPECT(usearch_size(index, &error) == 0);

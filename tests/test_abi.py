@@ -60,8 +60,11 @@ def test_init_and_metadata_without_gpu():
     index = Index(ndim=64, metric="cos", dtype="f32", connectivity=16, expansion_search=77)
     assert index.ndim == 64 and index.connectivity == 16 and index.expansion_search == 77 and index.size == 0
     assert index.hardware_acceleration == "sm_100a"
-    with pytest.raises(RuntimeError, match="frozen"):
-        index.add(1, np.zeros(64, dtype=np.float32))
+    import torch
+    if not torch.cuda.is_available():  # mutation needs the device just like search does: no CPU fallback
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            index.add(1, np.zeros(64, dtype=np.float32))
+        assert not index.contains(1) and index.count(1) == 0 and index.get(1) is None
     with pytest.raises(RuntimeError):  # unsupported pair must be refused at init (c/lib.cpp:164-167)
         Index(ndim=64, metric="haversine", dtype="f32")
 

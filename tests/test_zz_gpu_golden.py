@@ -16,10 +16,6 @@ GOLDEN_FIXTURES = sorted(glob.glob(os.path.join(common.GOLDEN, "*_n*.npz")))
 IDS = [os.path.basename(p)[:-4] for p in GOLDEN_FIXTURES]
 
 
-# Opt-in like the rest of this file: none of these has been seen green on hardware yet (see the note below). The same
-# comparison - GPU results of `usearch_search` against the fixture's reference outputs - is part of the default suite
-# through the C client (tests/test_native_clients.py, fixture cos_f32_n2000_d64).
-@pytest.mark.skipif(os.environ.get("USEARCH_B200_TEST_EXPERIMENTAL") != "1", reason="opt-in: USEARCH_B200_TEST_EXPERIMENTAL=1")
 @pytest.mark.parametrize("path", GOLDEN_FIXTURES, ids=IDS)
 def test_search_matches_golden(path):
     """Labels, distance bits, counts and both counters of the graph search."""
@@ -34,9 +30,9 @@ def test_search_matches_golden(path):
     assert np.array_equal(got.keys, g["keys_native"])
 
 
-# Written after the round's GPU budget was spent: the one attempt to run it ended in the job's time limit before this
-# test reported (cause not established - see DESIGN.md §8 "open items"), so it stays opt-in until it has been seen green.
-@pytest.mark.skipif(os.environ.get("USEARCH_B200_TEST_EXPERIMENTAL") != "1", reason="opt-in: USEARCH_B200_TEST_EXPERIMENTAL=1")
+# Round 1 never saw this test finish: cluster(level = top) on a graph whose top level holds ONE member walks an empty
+# list, and an empty list used to arm an mbarrier phase nobody waited for (search_kernel.cu, measure_list) - the next
+# wait of that warp deadlocked. Fixed in round 2; the case below (levels up to and beyond the top) is the regression test.
 @pytest.mark.parametrize("path", GOLDEN_FIXTURES, ids=IDS)
 def test_next_rows_match_golden(path):
     """Exact search (index mode and free function) and cluster against tests/golden/next_rows.npz."""
@@ -65,40 +61,26 @@ def test_next_rows_match_golden(path):
     assert np.array_equal(free.keys[unique], wk[:, :k][unique])
 
 
-@pytest.mark.parametrize("flags,metric,scalar,n,d,m,ef,k,nq", [
-    ("HALF_WORDS", "cos", "f16", 6000, 768, 32, 128, 10, 128),
-    ("HALF_WORDS", "l2sq", "f16", 4000, 200, 16, 64, 10, 128),     # 400-byte vectors: ragged last chunk group
-    ("HALF_WORDS", "ip", "bf16", 4000, 256, 16, 64, 10, 128),
-    ("HALF_WORDS", "cos", "bf16", 3000, 136, 16, 300, 20, 64),     # ef > 256: shared-memory `top`
-    ("STAGED_DENSE", "ip", "i8", 8000, 1024, 16, 128, 10, 256),    # 16 resident warps per SM
-    ("STAGED_DENSE", "cos", "i8", 4000, 256, 16, 64, 10, 128),
-    ("STAGED_DENSE,STAGE_SETS=1", "l2sq", "i8", 4000, 512, 16, 64, 10, 128),
-    ("HALF_WORDS,STAGED_DENSE", "cos", "f16", 6000, 768, 32, 256, 10, 128),
+@pytest.mark.parametrize("metric,scalar,n,d,m,ef,k,nq", [
+    ("cos", "f16", 6000, 768, 32, 128, 10, 128),     # WORD metrics: 4 lanes per vector split by accumulator
+    ("l2sq", "f16", 4000, 200, 16, 64, 10, 128),     # 400-byte vectors: ragged last chunk group
+    ("ip", "bf16", 4000, 256, 16, 64, 10, 128),
+    ("cos", "bf16", 3000, 136, 16, 300, 20, 64),     # ef > 256: shared-memory `top`
+    ("ip", "i8", 8000, 1024, 16, 128, 10, 256),      # 16 resident warps per SM, one stage set
+    ("cos", "i8", 4000, 256, 16, 64, 10, 128),
+    ("l2sq", "i8", 4000, 512, 16, 64, 10, 128),
+    ("cos", "f16", 6000, 768, 32, 256, 10, 128),     # C3's ef
+    ("cos", "f16", 3000, 1536, 16, 64, 10, 64),      # 3 KB half vectors: two stage sets again
+    ("ip", "i8", 3000, 4096, 16, 64, 10, 64),        # 4 KB i8 vectors
 ])
-@pytest.mark.skipif(os.environ.get("USEARCH_B200_TEST_EXPERIMENTAL") != "1",
-                    reason="opt-in (USEARCH_B200_TEST_EXPERIMENTAL=1): these variants have not run on hardware yet")
-def test_experimental_variants_match_reference(flags, metric, scalar, n, d, m, ef, k, nq):
-    """The off-by-default kernel variants (USEARCH_B200_HALF_WORDS: f16/bf16 with 4 lanes per vector split by
-    accumulator; USEARCH_B200_STAGED_DENSE: 16 resident warps per SM) against the reference. The switches are read once
-    per process, hence the subprocess."""
-    import subprocess
-    import sys
-    code = (
-        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
-        "import numpy as np, common\n"
-        "from oracle import bindings\n"
-        "from usearch_b200.index import Index\n"
-        "base, q = common.make_collection(%d, %d, %r, %d)\n"
-        "ref, blob = common.build_reference_blob(base, %r, %r, %d, %d, threads=16)\n"
-        "want = bindings.PortIndex(blob, %d).search(q, %d, threads=16)\n"
-        "index = Index.restore(blob); index.expansion_search = %d\n"
-        "got = index.search(q, %d, stats=True)\n"
-        "common.assert_same_results(want, (got.keys, got.distances, got.counts, index.last_computed, index.last_visited), 'variant')\n"
-        "print('VARIANT_OK')\n"
-    ) % (common.ROOT, os.path.join(common.ROOT, "tests"), n, d, scalar, nq, metric, scalar, d, m, ef, k, ef, k)
-    env = dict(os.environ)
-    for flag in flags.split(","):
-        name, _, value = flag.partition("=")
-        env["USEARCH_B200_" + name] = value or "1"
-    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
-    assert out.returncode == 0 and "VARIANT_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+def test_short_vector_kernels_match_reference(metric, scalar, n, d, m, ef, k, nq):
+    """The kernels that became the default in round 2 for f16 / bf16 / i8 (search_kernel.cu, dispatch) against the pinned
+    oracle on a reference-built graph: labels, distance bits, counts, both counters."""
+    from usearch_b200.index import Index
+    base, q = common.make_collection(n, d, scalar, nq)
+    ref, blob = common.build_reference_blob(base, metric, scalar, d, m, threads=16)
+    want = bindings.PortIndex(blob, ef).search(q, k, threads=16)
+    index = Index.restore(blob)
+    index.expansion_search = ef
+    got = index.search(q, k, stats=True)
+    common.assert_same_results(want, (got.keys, got.distances, got.counts, index.last_computed, index.last_visited), "gpu vs oracle")

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libusearch_b200.so")
-SOURCES = ["c_abi.cu", "frozen_index.cu", "search_kernel.cu", "exact_kernel.cu", "exact_imma.cu"]
+SOURCES = ["c_abi.cu", "frozen_index.cu", "search_kernel.cu", "exact_kernel.cu", "exact_imma.cu", "builder.cu"]
 HEADERS = ["device_index.h", "frozen_index.h", "metrics.cuh", "warp_primitives.cuh", "exact_args.h", os.path.join("..", "..", "include", "usearch_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
@@ -32,8 +32,7 @@ def _stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return OUT
-    objs = []
-    for src in SOURCES:
+    def compile_one(src: str) -> str:
         obj = os.path.join(CSRC, src.replace(".cu", ".o"))
         cmd = [NVCC, *[f for f in FLAGS if f not in ("--shared",)], "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose and src == "search_kernel.cu":
@@ -44,7 +43,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f"nvcc failed on {src}")
         if verbose:
             sys.stderr.write(proc.stderr)
-        objs.append(obj)
+        return obj
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:  # one nvcc per translation unit, side by side
+        objs = list(pool.map(compile_one, SOURCES))
     cmd = [NVCC, "--shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT, *objs]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:

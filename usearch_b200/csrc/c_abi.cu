@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <cstring>
 #include <new>
+#include <vector>
 
 #include "../../include/usearch_b200.h"
 #include "frozen_index.h"
@@ -21,8 +22,6 @@
 using namespace usearch_b200;
 
 namespace {
-
-char const* const FROZEN = "Index is frozen in GPU memory: build or modify it with the host library, then load it";
 
 uint32_t metric_to_char(usearch_metric_kind_t kind) { /* c/lib.cpp:26-40 */
     switch (kind) {
@@ -139,8 +138,7 @@ usearch_index_t usearch_init(usearch_init_options_t* options, usearch_error_t* e
         set_error(error, "Out of memory!");
         return nullptr;
     }
-    if (char const* dev = std::getenv("USEARCH_B200_DEVICE")) index->device = std::atoi(dev);
-    else if (char const* rank = std::getenv("LOCAL_RANK")) index->device = std::atoi(rank);
+    index->device = default_device();
     if (!options) return index; /* c/lib.cpp:142-147: empty index awaiting `load` */
     if (options->metric) {
         set_error(error, "Custom host metrics cannot run on the device");
@@ -217,10 +215,14 @@ void usearch_save(usearch_index_t index, char const* path, usearch_error_t* erro
 }
 
 size_t usearch_size(usearch_index_t index, usearch_error_t*) { return as_index(index)->size - as_index(index)->count_deleted; }
-size_t usearch_capacity(usearch_index_t index, usearch_error_t*) { return as_index(index)->size; }
+size_t usearch_capacity(usearch_index_t index, usearch_error_t*) { return std::max(as_index(index)->capacity, as_index(index)->size); }
 size_t usearch_dimensions(usearch_index_t index, usearch_error_t*) { return as_index(index)->dimensions; }
 size_t usearch_connectivity(usearch_index_t index, usearch_error_t*) { return as_index(index)->connectivity; }
-void usearch_reserve(usearch_index_t, size_t, usearch_error_t*) {}
+void usearch_reserve(usearch_index_t index, size_t capacity, usearch_error_t* error) { /* c/lib.cpp:365-370 */
+    frozen_index_t* ix = as_index(index);
+    std::lock_guard<std::mutex> lock(ix->mutex);
+    set_error(error, ix->reserve_slots(capacity));
+}
 size_t usearch_expansion_add(usearch_index_t index, usearch_error_t*) { return as_index(index)->expansion_add; }
 size_t usearch_expansion_search(usearch_index_t index, usearch_error_t*) { return as_index(index)->expansion_search; }
 void usearch_change_expansion_add(usearch_index_t index, size_t expansion, usearch_error_t*) { as_index(index)->expansion_add = expansion; }
@@ -249,23 +251,37 @@ size_t usearch_search(usearch_index_t index, void const* query, usearch_scalar_k
     uint32_t qs = scalar_to_char(query_kind);
     if (!qs) { set_error(error, "Unknown scalar kind!"); return 0; }
     size_t total = 0;
-    size_t qbytes = (ix->dimensions * bits_per_scalar(qs) + 7) / 8;
-    if (char const* e = ix->search_host(query, 1, qbytes, qs, count, keys, count * 8, distances, count * 4, nullptr,
-                                        nullptr, nullptr, &total)) {
+    /* concurrent single-query callers are coalesced into one launch (frozen_index_t::search_single) */
+    if (char const* e = ix->search_single(query, qs, count, keys, distances, &total)) {
         set_error(error, e);
         return 0;
     }
     return total;
 }
 
+/* usearch.h:391-395, c/lib.cpp:413-429. A host callback cannot run inside the kernel; it is evaluated on the host once per
+ * live key (the reference evaluates it lazily, per candidate: the same answers for a pure predicate) and the resulting key
+ * set is applied on the device where the reference applies the callback (index_dense.hpp:2078-2083, index.hpp:4201/4236). */
 size_t usearch_filtered_search(usearch_index_t index, void const* query, usearch_scalar_kind_t query_kind, size_t count,
-                               int (*filter)(usearch_key_t, void*), void*, usearch_key_t* keys,
+                               int (*filter)(usearch_key_t, void*), void* filter_state, usearch_key_t* keys,
                                usearch_distance_t* distances, usearch_error_t* error) {
-    if (filter) {
-        set_error(error, "Host predicates cannot run on the device");
+    if (!filter) return usearch_search(index, query, query_kind, count, keys, distances, error);
+    frozen_index_t* ix = as_index(index);
+    uint32_t qs = scalar_to_char(query_kind);
+    if (!qs) { set_error(error, "Unknown scalar kind!"); return 0; }
+    std::vector<uint64_t> allowed;
+    {
+        std::lock_guard<std::mutex> lock(ix->mutex);
+        for (uint64_t key : ix->host_keys)
+            if (key != ix->free_key && filter(key, filter_state)) allowed.push_back(key);
+    }
+    size_t total = 0;
+    if (char const* e = ix->search_host(query, 1, 0, qs, count, keys, count * 8, distances, count * 4, nullptr, nullptr,
+                                        nullptr, &total, allowed.data(), allowed.size(), true)) {
+        set_error(error, e);
         return 0;
     }
-    return usearch_search(index, query, query_kind, count, keys, distances, error);
+    return total;
 }
 
 size_t usearch_search_many(usearch_index_t index, void const* queries, size_t queries_count, size_t queries_stride,
@@ -322,23 +338,92 @@ void usearch_b200_search_many_device(usearch_index_t index, void const* queries,
                                      uint32_t* computed_distances, uint32_t* visited_members, void* cuda_stream,
                                      usearch_error_t* error) {
     frozen_index_t* ix = as_index(index);
-    if (char const* e = ix->ensure_context()) return set_error(error, e);
     std::lock_guard<std::mutex> lock(ix->mutex);
+    if (char const* e = ix->ensure_context()) return set_error(error, e);
     cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ix->stream;
     set_error(error, ix->search_device(queries, queries_count, queries_stride, count, keys, distances, counts,
                                        computed_distances, visited_members, s));
 }
 
-void usearch_add(usearch_index_t, usearch_key_t, void const*, usearch_scalar_kind_t, usearch_error_t* error) { set_error(error, FROZEN); }
-bool usearch_contains(usearch_index_t, usearch_key_t, usearch_error_t* error) { set_error(error, FROZEN); return false; }
-size_t usearch_count(usearch_index_t, usearch_key_t, usearch_error_t* error) { set_error(error, FROZEN); return 0; }
-size_t usearch_get(usearch_index_t, usearch_key_t, size_t, void*, usearch_scalar_kind_t, usearch_error_t* error) { set_error(error, FROZEN); return 0; }
-size_t usearch_remove(usearch_index_t, usearch_key_t, usearch_error_t* error) { set_error(error, FROZEN); return 0; }
-size_t usearch_rename(usearch_index_t, usearch_key_t, usearch_key_t, usearch_error_t* error) { set_error(error, FROZEN); return 0; }
-usearch_distance_t usearch_distance(void const*, void const*, usearch_scalar_kind_t, size_t, usearch_metric_kind_t, usearch_error_t* error) {
-    set_error(error, "Scalar distances are not offloaded: call the host library");
-    return 0;
+/* c/lib.cpp:378-386 -> index_dense_gt::add (index_dense.hpp:760-765, :2002-2050). One member per call goes through the same
+ * batched builder as usearch_b200_add_many (a batch of one): correct, but the throughput entry is the batch call. */
+void usearch_add(usearch_index_t index, usearch_key_t key, void const* vector, usearch_scalar_kind_t kind, usearch_error_t* error) {
+    frozen_index_t* ix = as_index(index);
+    uint32_t const vs = scalar_to_char(kind);
+    if (!vs) return set_error(error, "Unknown scalar kind!");
+    std::lock_guard<std::mutex> lock(ix->mutex);
+    set_error(error, ix->add_many(&key, vector, 1, 0, vs, false));
 }
+
+void usearch_b200_add_many(usearch_index_t index, usearch_key_t const* keys, void const* vectors, size_t count, size_t vectors_stride,
+                           usearch_scalar_kind_t kind, usearch_error_t* error) {
+    frozen_index_t* ix = as_index(index);
+    uint32_t const vs = scalar_to_char(kind);
+    if (!vs) return set_error(error, "Unknown scalar kind!");
+    std::lock_guard<std::mutex> lock(ix->mutex);
+    set_error(error, ix->add_many(keys, vectors, count, vectors_stride, vs, false));
+}
+
+void usearch_b200_add_many_device(usearch_index_t index, usearch_key_t const* keys, void const* vectors, size_t count,
+                                  size_t vectors_stride, usearch_scalar_kind_t kind, usearch_error_t* error) {
+    frozen_index_t* ix = as_index(index);
+    uint32_t const vs = scalar_to_char(kind);
+    if (!vs) return set_error(error, "Unknown scalar kind!");
+    std::lock_guard<std::mutex> lock(ix->mutex);
+    set_error(error, ix->add_many(keys, vectors, count, vectors_stride, vs, true));
+}
+
+bool usearch_contains(usearch_index_t index, usearch_key_t key, usearch_error_t*) { /* c/lib.cpp:388-391 */
+    frozen_index_t* ix = as_index(index);
+    std::lock_guard<std::mutex> lock(ix->mutex);
+    ix->build_key_map();
+    return ix->key_map.contains(key);
+}
+
+size_t usearch_count(usearch_index_t index, usearch_key_t key, usearch_error_t*) { /* c/lib.cpp:393-396 */
+    frozen_index_t* ix = as_index(index);
+    std::lock_guard<std::mutex> lock(ix->mutex);
+    ix->build_key_map();
+    return ix->key_map.count(key);
+}
+
+size_t usearch_get(usearch_index_t index, usearch_key_t key, size_t count, void* vectors, usearch_scalar_kind_t kind,
+                   usearch_error_t* error) { /* c/lib.cpp:431-437 */
+    frozen_index_t* ix = as_index(index);
+    uint32_t const vs = scalar_to_char(kind);
+    if (!vs) { set_error(error, "Unknown scalar kind!"); return 0; }
+    std::lock_guard<std::mutex> lock(ix->mutex);
+    size_t found = 0;
+    set_error(error, ix->get_vectors(key, count, vectors, vs, &found));
+    return found;
+}
+
+size_t usearch_remove(usearch_index_t index, usearch_key_t key, usearch_error_t* error) { /* c/lib.cpp:439-446 */
+    frozen_index_t* ix = as_index(index);
+    std::lock_guard<std::mutex> lock(ix->mutex);
+    size_t removed = 0;
+    set_error(error, ix->remove_key(key, &removed));
+    return removed;
+}
+
+size_t usearch_rename(usearch_index_t index, usearch_key_t from, usearch_key_t to, usearch_error_t* error) { /* c/lib.cpp:448-455 */
+    frozen_index_t* ix = as_index(index);
+    std::lock_guard<std::mutex> lock(ix->mutex);
+    size_t renamed = 0;
+    set_error(error, ix->rename_key(from, to, &renamed));
+    return renamed;
+}
+
+/* c/lib.cpp:458-466: one distance between two caller vectors, through the metric structs the search kernels use */
+usearch_distance_t usearch_distance(void const* a, void const* b, usearch_scalar_kind_t kind, size_t dimensions,
+                                    usearch_metric_kind_t metric_kind, usearch_error_t* error) {
+    uint32_t const m = metric_to_char(metric_kind), sc = scalar_to_char(kind);
+    if (!m || !sc || !search_supported(m, sc)) { set_error(error, "Unknown metric kind!"); return 0; }
+    float result = 0;
+    set_error(error, pair_distance_host(a, b, sc, dimensions, m, &result));
+    return result;
+}
+
 void usearch_exact_search(void const* dataset, size_t dataset_size, size_t dataset_stride, void const* queries, size_t queries_size,
                           size_t queries_stride, usearch_scalar_kind_t scalar_kind, size_t dimensions, usearch_metric_kind_t metric_kind,
                           size_t count, size_t /*threads*/, usearch_key_t* keys, size_t keys_stride, usearch_distance_t* distances,
@@ -357,7 +442,6 @@ void usearch_b200_cluster_many(usearch_index_t index, void const* queries, size_
     frozen_index_t* ix = as_index(index);
     uint32_t qs = scalar_to_char(query_kind);
     if (!qs) return set_error(error, "Unknown scalar kind!");
-    if (ix->loaded && ix->size == 0) return set_error(error, "No clusters to identify");
     set_error(error, ix->search_host(queries, queries_count, queries_stride, qs, 1, keys, 8, distances, 4, nullptr, computed_distances,
                                      visited_members, nullptr, nullptr, 0, false, (int)std::min<size_t>(level, 0x7FFF)));
 }

@@ -73,6 +73,11 @@ struct search_args_t {
     uint32_t const* query_list = nullptr; /* optional indirection (retries): work item i -> query id */
     uint32_t k = 0, ef = 0;
     int32_t cluster_end_level = -1; /* >= 0: index_gt::cluster — stop the descent above this level, report the closest member */
+    /* INSERT mode (GPU-assisted add, builder.cu): work item i runs search_to_insert_ (index.hpp:4010-4079) for the stored
+     * vector of slot query_list[i] on level task_levels[i]: greedy descent down to that level, then the best-first loop over
+     * that level's lists with no predicate. Results are SLOTS, one row per WORK ITEM: out_slots/out_dists [nq x k], out_counts [nq]. */
+    uint8_t const* task_levels = nullptr;
+    uint32_t* out_slots = nullptr;
     /* outputs, dense [nq x k] / [nq] indexed by query id */
     uint64_t* out_keys = nullptr;
     float* out_dists = nullptr;

@@ -43,6 +43,12 @@ char const* cuda_error(cudaError_t e) {
 
 } // namespace
 
+int default_device() {
+    if (char const* dev = std::getenv("USEARCH_B200_DEVICE")) return std::atoi(dev);
+    if (char const* rank = std::getenv("LOCAL_RANK")) return std::atoi(rank);
+    return 0;
+}
+
 size_t bits_per_scalar(uint32_t s) { /* index_plugins.hpp:237-257 */
     switch (s) {
     case SCALAR_B1: return 1;
@@ -60,6 +66,8 @@ frozen_index_t::~frozen_index_t() {
     if (ev_begin) cudaEventDestroy(ev_begin);
     if (ev_end) cudaEventDestroy(ev_end);
     phase_cycles.release();
+    build.release();
+    cast_stage.release();
     exact_scratch.release();
     visit_log.release();
     visited.release(); work_counter.release(); status.release(); counts.release(); computed.release();
@@ -79,7 +87,13 @@ void frozen_index_t::release_device() {
     loaded = false;
     size = 0;
     count_deleted = 0;
+    capacity = 0;
+    upper_capacity = 0;
+    upper_rows = 0;
+    visited_zeroed_words = 0;
     levels.clear();
+    host_keys.clear();
+    key_map.clear();
 }
 
 char const* frozen_index_t::ensure_context() {
@@ -149,14 +163,23 @@ char const* frozen_index_t::load_blob(uint8_t const* blob, size_t length) {
     uint8_t const* const levels_bytes = p;
     p += n * 2;
 
-    metric = head_metric;
-    scalar = head_scalar;
-    dimensions = dims;
-    connectivity = m;
-    connectivity_base = m0;
-    multi = head_multi;
-    size = n;
-    count_deleted = deleted;
+    /* host fields are committed only when the whole file has been accepted (see `commit` below) */
+    auto commit = [&](device_index_t const& accepted, size_t rows_in_upper) {
+        metric = head_metric;
+        scalar = head_scalar;
+        dimensions = dims;
+        connectivity = m;
+        connectivity_base = m0;
+        multi = head_multi;
+        size = n;
+        count_deleted = deleted;
+        capacity = n;
+        upper_rows = rows_in_upper;
+        upper_capacity = std::max<size_t>(rows_in_upper, 1);
+        d = accepted;
+        loaded = true;
+    };
+    if (n && max_level > 0x7FFF) return "File is corrupted: level out of range";
 
     device_index_t ix;
     ix.n = (uint32_t)n;
@@ -170,16 +193,23 @@ char const* frozen_index_t::load_blob(uint8_t const* blob, size_t length) {
     ix.bytes_per_vector = (uint32_t)bpv;
     ix.vec_stride = round_up((uint32_t)bpv, 16);
     ix.chunks16 = (uint32_t)(ix.vec_stride / 16);
-    ix.metric = metric;
-    ix.scalar = scalar;
+    ix.metric = head_metric;
+    ix.scalar = head_scalar;
     if (n == 0) {
-        d = ix;
-        loaded = true;
+        commit(ix, 0);
+        upper_capacity = 0;
         return nullptr;
     }
+    if (entry >= n) return "File is corrupted: entry slot out of range";
 
     /* pass 1: levels, upper row offsets, tape offsets */
     levels.resize(n);
+    host_keys.resize(n);
+    struct drop_host_state_t { /* a rejected file leaves no trace in the handle */
+        frozen_index_t* self;
+        bool armed = true;
+        ~drop_host_state_t() { if (armed) { self->levels.clear(); self->host_keys.clear(); self->release_device(); } }
+    } drop_host_state{this};
     std::vector<uint32_t> upper_base(n);
     uint64_t upper_rows = 0;
     size_t const nb = m * 4 + 4, nb0 = m0 * 4 + 4;
@@ -196,6 +226,8 @@ char const* frozen_index_t::load_blob(uint8_t const* blob, size_t length) {
             q += node_bytes;
         }
         if (upper_rows >= 0xFFFFFFFFull) return "Too many upper-level rows";
+        /* the descent starts on `max_level` at the entry point (index.hpp:3963-3975): it must own that many rows */
+        if ((uint64_t)levels[entry] != max_level) return "File is corrupted: entry point and top level disagree";
     }
 
     /* device allocations */
@@ -239,6 +271,7 @@ char const* frozen_index_t::load_blob(uint8_t const* blob, size_t length) {
         for (uint64_t i = begin; i < stop; ++i) {
             uint64_t key = rd_u64(q);
             h_keys[i - begin] = key;
+            host_keys[i] = key;
             if (key == free_key) { h_deleted[i >> 5] |= 1u << (i & 31); any_deleted = true; }
             uint8_t const* list = q + 10;
             uint32_t c0 = std::min<uint32_t>(rd_u32(list), (uint32_t)m0);
@@ -262,6 +295,8 @@ char const* frozen_index_t::load_blob(uint8_t const* blob, size_t length) {
                 for (uint32_t j = 0; j < c; ++j) {
                     uint32_t s = rd_u32(list + 4 + 4 * j);
                     if (s >= n) return "File is corrupted: neighbour slot out of range";
+                    /* a search on level l+1 reads row l+1 of every member it reaches: the member must have it */
+                    if (levels[s] < l + 1) return "File is corrupted: link to a member that is absent from that level";
                     dst[j] = s;
                 }
             }
@@ -279,15 +314,13 @@ char const* frozen_index_t::load_blob(uint8_t const* blob, size_t length) {
         CU(cudaMemcpy(d_deleted, h_deleted.data(), bytes_deleted, cudaMemcpyHostToDevice));
         hbm_bytes += bytes_deleted;
     }
-    if (entry >= n) return "File is corrupted: entry slot out of range";
-
     ix.vectors = d_vectors;
     ix.keys = d_keys;
     ix.nbr0 = d_nbr0;
     ix.upper_base = d_upper_base;
     ix.upper = d_upper;
     ix.deleted_bits = d_deleted;
-    if (search_needs_norms(metric, scalar)) {
+    if (search_needs_norms(head_metric, head_scalar)) {
         float* d_norms = nullptr;
         CU(cudaMalloc(&d_norms, (size_t)n * 4)); dev_allocs[6] = d_norms;
         hbm_bytes += (size_t)n * 4;
@@ -295,8 +328,8 @@ char const* frozen_index_t::load_blob(uint8_t const* blob, size_t length) {
         CU(cudaStreamSynchronize(stream));
         ix.norms = d_norms;
     }
-    d = ix;
-    loaded = true;
+    drop_host_state.armed = false;
+    commit(ix, upper_rows);
     return nullptr;
 }
 
@@ -374,10 +407,13 @@ char const* frozen_index_t::save_blob(uint8_t* out, size_t length) const {
 /*  launch planning                                                                               */
 /* ---------------------------------------------------------------------------------------------- */
 
-char const* frozen_index_t::plan(uint32_t k, uint32_t visited_cap_override, launch_plan_t& pl) const {
+char const* frozen_index_t::plan(uint32_t k, uint32_t visited_cap_override, launch_plan_t& pl, uint32_t ef_override) const {
     uint32_t ef = (uint32_t)(expansion_search ? expansion_search : 64); /* index.hpp:3029-3030 */
     ef = std::max(ef, k);                                               /* index.hpp:3052 */
+    if (ef_override) ef = ef_override; /* the builder searches with expansion_add (index.hpp:2854) */
     pl.ef = ef;
+    /* `visits` covers every slot the arrays have room for, so that its size does not change while members are added */
+    uint64_t const visit_slots = std::max<uint64_t>(capacity, d.n);
     uint32_t const list_cap = round_up(std::max(d.m0, d.m), 32);
     /* per-warp (= per-CTA) shared memory: query | top | candidates | mbarriers | TMA slots | heap head */
     uint32_t off = 0;
@@ -416,16 +452,18 @@ char const* frozen_index_t::plan(uint32_t k, uint32_t visited_cap_override, laun
         pl.stage_stride = round_up(pl.stage_seg_chunks * 16, 128) + search_stage_pad(d);
         /* double-buffer the slots when at least 4 warps per SM still fit */
         size_t const two = off + 2 * (size_t)slots * pl.stage_stride + min_heap + cta_tax;
-        pl.stage_sets = (forced_sets == 1 || forced_sets == 2) ? (uint32_t)forced_sets : (smem_sm / two >= 4 ? 2u : 1u);
-        if (slots > 16) pl.stage_sets = 1; /* one lane per vector: 32 slots in a single set */
-        if (segs == 2) pl.stage_sets = 2;  /* the two halves of a pass alternate between the two sets */
+        pl.stage_sets = smem_sm / two >= 4 ? 2u : 1u;
+        /* short vectors of the 16-warp kernels: resident warps beat double buffering (search_kernel.cu, dispatch) */
+        if (search_single_stage_set(d)) pl.stage_sets = 1;
+        if (forced_sets == 1 || forced_sets == 2) pl.stage_sets = (uint32_t)forced_sets;
+        if (segs == 2) pl.stage_sets = 2; /* the two halves of a pass alternate between the two sets */
     }
     off += (uint32_t)slots * pl.stage_sets * pl.stage_stride;
     pl.off_heap = off;
     uint32_t const fixed = off;
     if (fixed + min_heap > smem_cta_max) return "Expansion or dimensionality too large for on-chip state";
     static int const forced_warps = [] { char const* v = std::getenv("USEARCH_B200_WARPS_PER_SM"); return v ? std::atoi(v) : 0; }();
-    uint32_t warps_sm = (uint32_t)std::min<size_t>(smem_sm / (fixed + min_heap + cta_tax), slots ? 16 : 24);
+    uint32_t warps_sm = (uint32_t)std::min<size_t>(smem_sm / (fixed + min_heap + cta_tax), (size_t)search_max_warps_per_sm(d));
     if (forced_warps > 0) warps_sm = std::min<uint32_t>(warps_sm, (uint32_t)forced_warps);
     warps_sm = std::max(warps_sm, 1u);
     uint32_t budget = (uint32_t)(smem_sm / warps_sm - cta_tax);
@@ -438,7 +476,7 @@ char const* frozen_index_t::plan(uint32_t k, uint32_t visited_cap_override, laun
 
     /* scratch per warp. `scale` (1, 8, 64, ...) grows it for the retry of overflowed queries. */
     uint64_t const scale = visited_cap_override ? visited_cap_override : 1;
-    uint64_t const enough = (uint64_t)2 * ((uint64_t)d.n + d.m0 + 1); /* a hash table this large can never overflow */
+    uint64_t const enough = (uint64_t)2 * (visit_slots + d.m0 + 1); /* a hash table this large can never overflow */
     static int const forced = [] { /* test hook: USEARCH_B200_VISITED=hash|bitmap|bitmap_log */
         char const* v = std::getenv("USEARCH_B200_VISITED");
         return !v ? 0 : (std::strcmp(v, "hash") == 0 ? 1 : (std::strcmp(v, "bitmap") == 0 ? 2 : (std::strcmp(v, "bitmap_log") == 0 ? 3 : 0)));
@@ -447,19 +485,19 @@ char const* frozen_index_t::plan(uint32_t k, uint32_t visited_cap_override, laun
         char const* v = std::getenv("USEARCH_B200_SCRATCH_SHRINK");
         return v && std::atoi(v) > 0 ? (uint64_t)std::atoi(v) : (uint64_t)1;
     }();
-    uint64_t const bitmap_words = round_up((d.n + 31) / 32, 4);
+    uint64_t const bitmap_words = round_up((uint32_t)((visit_slots + 31) / 32), 4);
     uint64_t const max_warps_guess = (uint64_t)sm_count * 32;
     bool const bitmaps_fit = bitmap_words * 4 * std::min<uint64_t>(max_warps_guess, (uint64_t)sm_count * pl.warps_per_sm_target) <= BITMAP_SCRATCH_BUDGET;
     if (forced == 2 || forced == 3 || (forced == 0 && bitmaps_fit)) {
         /* BITMAP visits: one bit per slot, exact, never overflows */
         pl.visited_bitmap_words = (uint32_t)bitmap_words;
         pl.visited_cap = 0;
-        pl.visit_log_cap = (forced == 3 || (forced == 0 && (uint64_t)d.n > BITMAP_WIPE_MAX_SLOTS))
+        pl.visit_log_cap = (forced == 3 || (forced == 0 && visit_slots > BITMAP_WIPE_MAX_SLOTS))
                                ? (uint32_t)std::max<uint64_t>(32768 / shrink, 64) : 0u;
         uint64_t spill = std::max<uint64_t>(1024, (uint64_t)8 * ef) * scale / shrink;
         spill = std::max<uint64_t>(spill, 16);
-        pl.heap_spill_cap = (uint32_t)std::min<uint64_t>(spill, (uint64_t)d.n + 1);
-        pl.maxed = pl.heap_spill_cap >= d.n;
+        pl.heap_spill_cap = (uint32_t)std::min<uint64_t>(spill, visit_slots + 1);
+        pl.maxed = pl.heap_spill_cap >= visit_slots;
     } else {
         pl.visited_bitmap_words = 0;
         pl.visit_log_cap = 0;
@@ -482,55 +520,24 @@ char const* frozen_index_t::plan(uint32_t k, uint32_t visited_cap_override, laun
 /*  batched search on device buffers                                                              */
 /* ---------------------------------------------------------------------------------------------- */
 
-char const* frozen_index_t::search_device(void const* d_queries, size_t nq, size_t stride, size_t k, uint64_t* d_keys,
-                                          float* d_dists, uint32_t* d_counts, uint32_t* d_computed, uint32_t* d_cycles,
-                                          cudaStream_t s) {
-    if (!loaded) return "Index is empty: load a serialized index first";
-    if (nq == 0 || k == 0) return nullptr;
-    if (nq > 0x7FFFFFFFull) return "Too many queries in one batch";
-    CU(cudaSetDevice(device));
-    launch_plan_t pl;
-    if (char const* e = plan((uint32_t)k, 0, pl)) return e;
-    /* a small batch does not need the whole grid */
-    int const wpb = search_warps_per_block();
-    int blocks = (int)std::min<size_t>((size_t)pl.blocks, (nq + wpb - 1) / wpb);
-    size_t warps = (size_t)blocks * wpb;
-
+/* scratch for `warps` resident warps under plan `pl`, and the launch arguments that describe it */
+char const* frozen_index_t::prepare_launch(launch_plan_t const& pl, size_t warps, search_args_t& a, cudaStream_t s) {
     if (char const* e = work_counter.reserve(2)) return e;
-    if (char const* e = status.reserve(nq)) return e;
-    if (char const* e = h_status.reserve(nq)) return e;
-    auto reserve_visits = [&](launch_plan_t const& p, size_t nwarps) -> char const* {
-        size_t const words = nwarps * p.visited_words_per_warp();
-        bool const grown = words > visited.capacity;
-        if (char const* e = visited.reserve(words)) return e;
-        if (grown) visited_zeroed_words = 0;
-        if (p.visit_log_cap) { /* logged bitmaps rely on an all-zero slab between queries */
-            if (char const* e = visit_log.reserve(nwarps * p.visit_log_cap)) return e;
-            if (visited_zeroed_words < words) {
-                if (cudaMemsetAsync(visited.ptr, 0, words * 4, s) != cudaSuccess) return "CUDA failure: memset";
-                visited_zeroed_words = words;
-            }
-        } else
-            visited_zeroed_words = 0; /* wiped per query with other contents in between */
-        return nullptr;
-    };
-    if (char const* e = reserve_visits(pl, warps)) return e;
+    size_t const words = warps * pl.visited_words_per_warp();
+    bool const grown = words > visited.capacity;
+    if (char const* e = visited.reserve(words)) return e;
+    if (grown) visited_zeroed_words = 0;
+    if (pl.visit_log_cap) { /* logged bitmaps rely on an all-zero slab between queries */
+        if (char const* e = visit_log.reserve(warps * pl.visit_log_cap)) return e;
+        if (visited_zeroed_words < words) {
+            if (cudaMemsetAsync(visited.ptr, 0, words * 4, s) != cudaSuccess) return "CUDA failure: memset";
+            visited_zeroed_words = words;
+        }
+    } else
+        visited_zeroed_words = 0; /* wiped per query with other contents in between */
     if (char const* e = heap_spill.reserve(warps * pl.heap_spill_cap)) return e;
-
-    search_args_t a;
-    a.queries = static_cast<uint8_t const*>(d_queries);
-    a.query_stride = stride;
-    a.nq = (uint32_t)nq;
-    a.k = (uint32_t)k;
+    a = search_args_t{};
     a.ef = pl.ef;
-    a.out_keys = d_keys;
-    a.out_dists = d_dists;
-    a.out_counts = d_counts;
-    a.out_computed = d_computed;
-    a.out_visited = d_cycles;
-    a.status = status.ptr;
-    a.allow_bits = active_allow_bits;
-    a.cluster_end_level = active_cluster_end_level;
     a.work_counter = work_counter.ptr;
     a.visited = visited.ptr;
     a.visited_cap = pl.visited_cap;
@@ -550,6 +557,42 @@ char const* frozen_index_t::search_device(void const* d_queries, size_t nq, size
     /* measured on B200 (1M x 768 f32): per-lane issue 9.67 ms, single-lane back-to-back issue 10.33 ms */
     static int const issue_per_lane = [] { char const* v = std::getenv("USEARCH_B200_ISSUE_PER_LANE"); return v ? std::atoi(v) : 1; }();
     a.issue_per_lane = (uint32_t)issue_per_lane;
+    return nullptr;
+}
+
+char const* frozen_index_t::search_device(void const* d_queries, size_t nq, size_t stride, size_t k, uint64_t* d_keys,
+                                          float* d_dists, uint32_t* d_counts, uint32_t* d_computed, uint32_t* d_cycles,
+                                          cudaStream_t s) {
+    if (nq == 0 || k == 0) return nullptr;
+    if (nq > 0x7FFFFFFFull) return "Too many queries in one batch";
+    if (char const* e = ensure_context()) return e;
+    if (!loaded || d.n == 0) { /* no matches, no error (index.hpp:3036-3037) */
+        CU(search_fill_empty(d_keys, d_dists, d_counts, d_computed, d_cycles, nq, k, s));
+        return nullptr;
+    }
+    launch_plan_t pl;
+    if (char const* e = plan((uint32_t)k, 0, pl)) return e;
+    /* a small batch does not need the whole grid */
+    int const wpb = search_warps_per_block();
+    int blocks = (int)std::min<size_t>((size_t)pl.blocks, (nq + wpb - 1) / wpb);
+    size_t warps = (size_t)blocks * wpb;
+
+    if (char const* e = status.reserve(nq)) return e;
+    if (char const* e = h_status.reserve(nq)) return e;
+    search_args_t a;
+    if (char const* e = prepare_launch(pl, warps, a, s)) return e;
+    a.queries = static_cast<uint8_t const*>(d_queries);
+    a.query_stride = stride;
+    a.nq = (uint32_t)nq;
+    a.k = (uint32_t)k;
+    a.out_keys = d_keys;
+    a.out_dists = d_dists;
+    a.out_counts = d_counts;
+    a.out_computed = d_computed;
+    a.out_visited = d_cycles;
+    a.status = status.ptr;
+    a.allow_bits = active_allow_bits;
+    a.cluster_end_level = active_cluster_end_level;
 
     if (profile_phases) {
         if (char const* e = phase_cycles.reserve(16)) return e;
@@ -581,23 +624,16 @@ char const* frozen_index_t::search_device(void const* d_queries, size_t nq, size
         int rblocks = (int)std::min<size_t>({(size_t)rp.blocks, (failed.size() + wpb - 1) / wpb, max_warps / wpb});
         rblocks = std::max(rblocks, 1);
         size_t rwarps = (size_t)rblocks * wpb;
-        if (char const* e = reserve_visits(rp, rwarps)) return e;
-        if (char const* e = heap_spill.reserve(rwarps * rp.heap_spill_cap)) return e;
         if (char const* e = retry_list.reserve(failed.size())) return e;
         CU(cudaMemcpyAsync(retry_list.ptr, failed.data(), failed.size() * 4, cudaMemcpyHostToDevice, s));
-        search_args_t r = a;
-        r.heap_smem_cap = rp.heap_smem_cap;
-        r.smem_per_warp = rp.smem_per_warp;
-        r.off_heap = rp.off_heap;
+        search_args_t r;
+        if (char const* e = prepare_launch(rp, rwarps, r, s)) return e;
+        r.queries = a.queries; r.query_stride = a.query_stride; r.k = a.k;
+        r.out_keys = a.out_keys; r.out_dists = a.out_dists; r.out_counts = a.out_counts;
+        r.out_computed = a.out_computed; r.out_visited = a.out_visited; r.status = a.status;
+        r.allow_bits = a.allow_bits; r.cluster_end_level = a.cluster_end_level; r.phase_cycles = a.phase_cycles;
         r.nq = (uint32_t)failed.size();
         r.query_list = retry_list.ptr;
-        r.visited = visited.ptr;
-        r.visited_cap = rp.visited_cap;
-        r.visited_bitmap_words = rp.visited_bitmap_words;
-        r.visit_log = rp.visit_log_cap ? visit_log.ptr : nullptr;
-        r.visit_log_cap = rp.visit_log_cap;
-        r.heap_spill = heap_spill.ptr;
-        r.heap_spill_cap = rp.heap_spill_cap;
         CU(cudaMemsetAsync(work_counter.ptr, 0, 8, s));
         CU(search_launch(d, r, rblocks, rp.smem_per_block, s));
         kernel_launches += 1;
@@ -700,33 +736,53 @@ char const* cast_queries(uint32_t from, uint32_t to, size_t dims, uint8_t const*
 /*  batched search on host buffers: H2D + kernel + D2H inside the call                            */
 /* ---------------------------------------------------------------------------------------------- */
 
+/* host rows of `query_scalar` -> `queries` on the device in the index's scalar kind, rows zero-padded to vec_stride. The cast
+ * (index_dense_gt::search_ casts every query with casts_.from_*, index_dense.hpp:2060-2066) runs on the device. */
+char const* frozen_index_t::upload_queries(void const* q, size_t nq, size_t stride, uint32_t query_scalar) {
+    size_t const vs = d.vec_stride ? d.vec_stride : 16, bpv = d.bytes_per_vector;
+    size_t const src_bytes = (dimensions * bits_per_scalar(query_scalar) + 7) / 8;
+    if (!src_bytes) return "Unknown scalar kind!";
+    if (stride < src_bytes) { /* single-query callers pass 0; rows can not overlap */
+        if (nq != 1 && stride != 0) return "Query stride is smaller than a vector";
+        stride = src_bytes;
+    }
+    if (query_scalar == scalar) {
+        if (vs != bpv) CU(cudaMemsetAsync(queries.ptr, 0, nq * vs, stream));
+        CU(cudaMemcpy2DAsync(queries.ptr, vs, q, stride, bpv, nq, cudaMemcpyHostToDevice, stream));
+        return nullptr;
+    }
+    if (char const* e = cast_stage.reserve(nq * src_bytes)) return e;
+    CU(cudaMemcpy2DAsync(cast_stage.ptr, src_bytes, q, stride, src_bytes, nq, cudaMemcpyHostToDevice, stream));
+    return cast_rows_device(cast_stage.ptr, src_bytes, query_scalar, queries.ptr, vs, scalar, dimensions, nq, stream);
+}
+
 char const* frozen_index_t::search_host(void const* q, size_t nq, size_t stride, uint32_t query_scalar, size_t k,
                                         uint64_t* keys, size_t keys_stride, float* dists, size_t dists_stride,
                                         size_t* counts, uint64_t* computed_out, uint64_t* cycles_out, size_t* total,
                                         uint64_t const* allowed, size_t allowed_count, bool filtered, int cluster_level) {
     if (total) *total = 0;
-    if (!loaded) return "Index is empty: load a serialized index first";
     if (nq == 0 || k == 0) return nullptr;
-    if (char const* e = ensure_context()) return e;
     std::lock_guard<std::mutex> lock(mutex);
-    size_t const vs = d.vec_stride ? d.vec_stride : 16, bpv = d.bytes_per_vector;
+    if (!loaded || d.n == 0) { /* index_gt::search on an empty index: no matches, no error (index.hpp:3036-3037) */
+        if (cluster_level >= 0) return "No clusters to identify";
+        for (size_t i = 0; i < nq; ++i) {
+            uint64_t* krow = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(keys) + i * keys_stride);
+            uint32_t* drow = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(dists) + i * dists_stride);
+            for (size_t j = 0; j < k; ++j) { krow[j] = 0; drow[j] = SNAN_BITS; }
+            if (counts) counts[i] = 0;
+            if (computed_out) computed_out[i] = 0;
+            if (cycles_out) cycles_out[i] = 0;
+        }
+        return nullptr;
+    }
+    if (char const* e = ensure_context()) return e;
+    size_t const vs = d.vec_stride ? d.vec_stride : 16;
 
     if (char const* e = queries.reserve(nq * vs)) return e;
     if (char const* e = out_keys.reserve(nq * k)) return e;
     if (char const* e = out_dists.reserve(nq * k)) return e;
     if (char const* e = counts_reserve_all(nq)) return e;
-
-    /* queries -> device, rows padded to vec_stride */
-    if (vs != bpv) CU(cudaMemsetAsync(queries.ptr, 0, nq * vs, stream));
-    if (query_scalar == scalar) {
-        CU(cudaMemcpy2DAsync(queries.ptr, vs, q, stride, bpv, nq, cudaMemcpyHostToDevice, stream));
-    } else {
-        if (char const* e = h_queries.reserve(nq * vs)) return e;
-        if (char const* e = cast_queries(query_scalar, scalar, dimensions, static_cast<uint8_t const*>(q), stride, nq,
-                                         h_queries.ptr, vs))
-            return e;
-        CU(cudaMemcpy2DAsync(queries.ptr, vs, h_queries.ptr, vs, bpv, nq, cudaMemcpyHostToDevice, stream));
-    }
+    if (char const* e = upload_queries(q, nq, stride, query_scalar)) return e;
 
     /* filtered search: sort the allowed keys on the host, turn them into a bitmap over slots on the device */
     struct reset_filter_t {
@@ -778,6 +834,58 @@ char const* frozen_index_t::search_host(void const* q, size_t nq, size_t stride,
     return nullptr;
 }
 
+/* One query per call, many calling threads: gather what is waiting into one batch. The first caller to find no leader
+ * becomes it, takes every queued request of the same (scalar kind, count) as its own, runs them through search_host as one
+ * batch, hands the rows back and repeats until the queue is empty. */
+char const* frozen_index_t::search_single(void const* query, uint32_t query_scalar, size_t count, uint64_t* keys, float* dists,
+                                          size_t* found) {
+    single_request_t mine{query, query_scalar, count, keys, dists, 0, nullptr, false};
+    std::unique_lock<std::mutex> lock(gather_mutex);
+    gather_queue.push_back(&mine);
+    while (!mine.done && gather_leader) gather_cv.wait(lock);
+    if (mine.done) { *found = mine.found; return mine.error; }
+    gather_leader = true;
+    while (!gather_queue.empty()) {
+        /* the batch: every waiting request that matches the head's shape */
+        std::vector<single_request_t*> batch, rest;
+        for (single_request_t* r : gather_queue)
+            (r->scalar == gather_queue[0]->scalar && r->count == gather_queue[0]->count ? batch : rest).push_back(r);
+        gather_queue.swap(rest);
+        lock.unlock();
+        size_t const nq = batch.size(), k = batch[0]->count;
+        size_t const qbytes = (dimensions * bits_per_scalar(batch[0]->scalar) + 7) / 8;
+        char const* e = nullptr;
+        if (nq == 1) {
+            size_t total = 0;
+            e = search_host(batch[0]->query, 1, 0, batch[0]->scalar, k, batch[0]->keys, k * 8, batch[0]->dists, k * 4, nullptr, nullptr,
+                            nullptr, &total);
+            batch[0]->found = total;
+        } else {
+            std::vector<uint8_t> q(nq * qbytes);
+            std::vector<uint64_t> out_k(nq * k);
+            std::vector<float> out_d(nq * k);
+            std::vector<size_t> cnt(nq);
+            for (size_t i = 0; i < nq; ++i) std::memcpy(q.data() + i * qbytes, batch[i]->query, qbytes);
+            e = search_host(q.data(), nq, qbytes, batch[0]->scalar, k, out_k.data(), k * 8, out_d.data(), k * 4, cnt.data(), nullptr,
+                            nullptr, nullptr);
+            for (size_t i = 0; i < nq && !e; ++i) {
+                std::memcpy(batch[i]->keys, out_k.data() + i * k, k * 8);
+                std::memcpy(batch[i]->dists, out_d.data() + i * k, k * 4);
+                batch[i]->found = cnt[i];
+            }
+        }
+        lock.lock();
+        gathered_batches += 1;
+        gathered_queries += nq;
+        for (single_request_t* r : batch) { r->error = e; r->done = true; }
+        gather_cv.notify_all();
+    }
+    gather_leader = false;
+    gather_cv.notify_all(); /* a request that slipped in while the leader was leaving elects a new one */
+    *found = mine.found;
+    return mine.error;
+}
+
 /* ---------------------------------------------------------------------------------------------- */
 /*  exact (brute-force) search: host wrappers around exact_kernel.cu                              */
 /* ---------------------------------------------------------------------------------------------- */
@@ -785,23 +893,22 @@ char const* frozen_index_t::search_host(void const* q, size_t nq, size_t stride,
 /* index_gt::search(exact = true) (index.hpp:3047-3051 -> search_exact_ :4251-4268) for a batch of host queries */
 char const* frozen_index_t::exact_host(void const* q, size_t nq, size_t stride, uint32_t query_scalar, size_t k, uint64_t* keys,
                                        float* dists, size_t* counts_out) {
-    if (!loaded) return "Index is empty: load a serialized index first";
     if (nq == 0 || k == 0) return nullptr;
-    if (char const* e = ensure_context()) return e;
     std::lock_guard<std::mutex> lock(mutex);
-    size_t const vs = d.vec_stride ? d.vec_stride : 16, bpv = d.bytes_per_vector;
+    if (!loaded || d.n == 0) {
+        for (size_t i = 0; i < nq; ++i) {
+            for (size_t j = 0; j < k; ++j) { keys[i * k + j] = 0; reinterpret_cast<uint32_t*>(dists)[i * k + j] = SNAN_BITS; }
+            if (counts_out) counts_out[i] = 0;
+        }
+        return nullptr;
+    }
+    if (char const* e = ensure_context()) return e;
+    size_t const vs = d.vec_stride ? d.vec_stride : 16;
     if (char const* e = queries.reserve(nq * vs)) return e;
     if (char const* e = out_keys.reserve(nq * k)) return e;
     if (char const* e = out_dists.reserve(nq * k)) return e;
     if (char const* e = counts_reserve_all(nq)) return e;
-    if (vs != bpv) CU(cudaMemsetAsync(queries.ptr, 0, nq * vs, stream));
-    if (query_scalar == scalar) {
-        CU(cudaMemcpy2DAsync(queries.ptr, vs, q, stride, bpv, nq, cudaMemcpyHostToDevice, stream));
-    } else {
-        if (char const* e = h_queries.reserve(nq * vs)) return e;
-        if (char const* e = cast_queries(query_scalar, scalar, dimensions, static_cast<uint8_t const*>(q), stride, nq, h_queries.ptr, vs)) return e;
-        CU(cudaMemcpy2DAsync(queries.ptr, vs, h_queries.ptr, vs, bpv, nq, cudaMemcpyHostToDevice, stream));
-    }
+    if (char const* e = upload_queries(q, nq, stride, query_scalar)) return e;
     if (char const* e = exact_search_device(d, sm_count, queries.ptr, nq, vs, k, false, false, out_keys.ptr, out_dists.ptr, counts.ptr,
                                             exact_scratch, stream))
         return e;
@@ -824,7 +931,7 @@ char const* exact_search_free(void const* dataset, size_t n, size_t dataset_stri
     if (k > n) return "More neighbours requested than the dataset holds";
     if (n >= 0xFFFFFFFFull) return "Too many entries for 32-bit slots";
     frozen_index_t tmp;
-    if (char const* dev = std::getenv("USEARCH_B200_DEVICE")) tmp.device = std::atoi(dev);
+    tmp.device = default_device();
     if (char const* e = tmp.ensure_context()) return e;
     size_t const bpv = (dimensions * bits_per_scalar(scalar) + 7) / 8, vs = (bpv + 15) / 16 * 16;
     device_index_t ix;
@@ -867,6 +974,153 @@ char const* exact_search_free(void const* dataset, size_t n, size_t dataset_stri
     CU(cudaMemcpy2DAsync(keys, keys_stride, d_keys.ptr, k * 8, k * 8, nq, cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpy2DAsync(distances, distances_stride, d_dists.ptr, k * 4, k * 4, nq, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
+    return nullptr;
+}
+
+/* usearch_distance: both vectors to the device, one warp, the metric struct of the search kernels */
+char const* pair_distance_host(void const* a, void const* b, uint32_t scalar, size_t dimensions, uint32_t metric, float* result) {
+    frozen_index_t tmp;
+    tmp.device = default_device();
+    if (char const* e = tmp.ensure_context()) return e;
+    size_t const bpv = (dimensions * bits_per_scalar(scalar) + 7) / 8, vs = (bpv + 15) / 16 * 16;
+    if (vs > 48 * 1024) return "Vector too long for a single-pair distance";
+    device_index_t ix;
+    ix.dims = (uint32_t)dimensions;
+    ix.bytes_per_vector = (uint32_t)bpv;
+    ix.vec_stride = vs;
+    ix.chunks16 = (uint32_t)(vs / 16);
+    ix.metric = metric;
+    ix.scalar = scalar;
+    device_buffer_t<uint8_t> pair;
+    device_buffer_t<float> out;
+    struct release_t { device_buffer_t<uint8_t>& a; device_buffer_t<float>& b; ~release_t() { a.release(); b.release(); } } release{pair, out};
+    if (char const* e = pair.reserve(2 * vs)) return e;
+    if (char const* e = out.reserve(1)) return e;
+    CU(cudaMemsetAsync(pair.ptr, 0, 2 * vs, tmp.stream));
+    CU(cudaMemcpyAsync(pair.ptr, a, bpv, cudaMemcpyHostToDevice, tmp.stream));
+    CU(cudaMemcpyAsync(pair.ptr + vs, b, bpv, cudaMemcpyHostToDevice, tmp.stream));
+    if (char const* e = pair_distance_device(ix, pair.ptr, pair.ptr + vs, out.ptr, tmp.stream)) return e;
+    CU(cudaMemcpyAsync(result, out.ptr, 4, cudaMemcpyDeviceToHost, tmp.stream));
+    CU(cudaStreamSynchronize(tmp.stream));
+    return nullptr;
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/*  lookups and edits by key                                                                      */
+/* ---------------------------------------------------------------------------------------------- */
+
+/* index_dense_gt::remove (index_dense.hpp:1480-1513): the entry keeps its node and its links, its key becomes the free key
+ * (so searches skip it: `deleted_bits`), and the key leaves the lookup table. Slots are not recycled. */
+char const* frozen_index_t::remove_key(uint64_t key, size_t* removed) {
+    *removed = 0;
+    if (!loaded || !size) return nullptr;
+    if (char const* e = ensure_context()) return e;
+    build_key_map();
+    std::vector<uint32_t> slots;
+    key_map.for_each(key, [&](uint32_t slot, size_t cell) { slots.push_back(slot); key_map.erase_cell(cell); return true; });
+    if (slots.empty()) return nullptr;
+    if (!d.deleted_bits) {
+        uint32_t* bits = nullptr;
+        size_t const words = (capacity + 31) / 32;
+        CU(cudaMalloc(&bits, words * 4));
+        CU(cudaMemset(bits, 0, words * 4));
+        dev_allocs[5] = bits;
+        d.deleted_bits = bits;
+        hbm_bytes += words * 4;
+    }
+    for (uint32_t slot : slots) {
+        host_keys[slot] = free_key;
+        CU(cudaMemcpy(const_cast<uint64_t*>(d.keys) + slot, &free_key, 8, cudaMemcpyHostToDevice));
+        uint32_t word = 0;
+        CU(cudaMemcpy(&word, d.deleted_bits + (slot >> 5), 4, cudaMemcpyDeviceToHost));
+        word |= 1u << (slot & 31);
+        CU(cudaMemcpy(const_cast<uint32_t*>(d.deleted_bits) + (slot >> 5), &word, 4, cudaMemcpyHostToDevice));
+    }
+    count_deleted += slots.size();
+    *removed = slots.size();
+    return nullptr;
+}
+
+/* index_dense_gt::rename (index_dense.hpp:1554-1580): every entry under `from` gets the key `to` */
+char const* frozen_index_t::rename_key(uint64_t from, uint64_t to, size_t* renamed) {
+    *renamed = 0;
+    if (!loaded || !size) return nullptr;
+    if (char const* e = ensure_context()) return e;
+    if (to == free_key) return "Key is reserved for removed entries";
+    build_key_map();
+    if (!multi && key_map.contains(to)) return "Renaming impossible, the key is already in use";
+    std::vector<uint32_t> slots;
+    key_map.for_each(from, [&](uint32_t slot, size_t cell) { slots.push_back(slot); key_map.erase_cell(cell); return true; });
+    for (uint32_t slot : slots) {
+        host_keys[slot] = to;
+        key_map.insert(to, slot);
+        CU(cudaMemcpy(const_cast<uint64_t*>(d.keys) + slot, &to, 8, cudaMemcpyHostToDevice));
+    }
+    *renamed = slots.size();
+    return nullptr;
+}
+
+namespace {
+
+float half_bits_to_f32(uint16_t h) {
+    uint32_t const sign = (uint32_t)(h & 0x8000u) << 16, exp = (h >> 10) & 0x1Fu, mant = h & 0x3FFu;
+    uint32_t bits;
+    if (exp == 0) {
+        if (!mant) bits = sign;
+        else { /* subnormal: renormalise */
+            int e = -1;
+            uint32_t m = mant;
+            do { ++e; m <<= 1; } while (!(m & 0x400u));
+            bits = sign | ((uint32_t)(127 - 15 - e) << 23) | ((m & 0x3FFu) << 13);
+        }
+    } else if (exp == 31) bits = sign | 0x7F800000u | (mant << 13);
+    else bits = sign | ((exp + 112u) << 23) | (mant << 13);
+    float f;
+    std::memcpy(&f, &bits, 4);
+    return f;
+}
+
+/* one stored vector -> the caller's scalar kind (index_dense_gt::get_ casts with casts_.to_*, index_dense.hpp:2121-2150) */
+char const* cast_stored_row(uint32_t from, uint32_t to, size_t dims, uint8_t const* src, uint8_t* dst) {
+    size_t const to_bytes = (dims * bits_per_scalar(to) + 7) / 8;
+    if (from == to) { std::memcpy(dst, src, to_bytes); return nullptr; }
+    std::vector<float> row(dims);
+    for (size_t j = 0; j < dims; ++j) {
+        switch (from) {
+        case SCALAR_F32: std::memcpy(&row[j], src + 4 * j, 4); break;
+        case SCALAR_F16: { uint16_t h; std::memcpy(&h, src + 2 * j, 2); row[j] = half_bits_to_f32(h); break; }
+        case SCALAR_BF16: { uint16_t h; std::memcpy(&h, src + 2 * j, 2); uint32_t b = (uint32_t)h << 16; std::memcpy(&row[j], &b, 4); break; }
+        case SCALAR_I8: row[j] = (float)reinterpret_cast<int8_t const*>(src)[j] / 127.f; break;     /* cast_from_i8_gt */
+        case SCALAR_B1: row[j] = (src[j >> 3] & (128u >> (j & 7u))) ? 1.f : 0.f; break;            /* cast_from_b1x8_gt */
+        default: return "Unsupported scalar kind";
+        }
+    }
+    if (to == SCALAR_F64) {
+        for (size_t j = 0; j < dims; ++j) { double v = row[j]; std::memcpy(dst + 8 * j, &v, 8); }
+        return nullptr;
+    }
+    return cast_queries(SCALAR_F32, to, dims, reinterpret_cast<uint8_t const*>(row.data()), dims * 4, 1, dst, to_bytes);
+}
+
+} // namespace
+
+/* index_dense_gt::get (index_dense.hpp:781-786 -> get_ :2121-2150): up to `max_count` vectors stored under `key` */
+char const* frozen_index_t::get_vectors(uint64_t key, size_t max_count, void* out, uint32_t out_scalar, size_t* found) {
+    *found = 0;
+    if (!loaded || !size || !max_count) return nullptr;
+    if (char const* e = ensure_context()) return e;
+    size_t const out_bytes = (dimensions * bits_per_scalar(out_scalar) + 7) / 8;
+    if (!out_bytes) return "Unknown scalar kind!";
+    build_key_map();
+    std::vector<uint32_t> slots;
+    key_map.for_each(key, [&](uint32_t slot, size_t) { slots.push_back(slot); return slots.size() < max_count; });
+    std::sort(slots.begin(), slots.end()); /* insertion order */
+    std::vector<uint8_t> row(d.vec_stride);
+    for (size_t i = 0; i < slots.size(); ++i) {
+        CU(cudaMemcpy(row.data(), d.vectors + (size_t)slots[i] * d.vec_stride, d.bytes_per_vector, cudaMemcpyDeviceToHost));
+        if (char const* e = cast_stored_row(scalar, out_scalar, dimensions, row.data(), static_cast<uint8_t*>(out) + i * out_bytes)) return e;
+    }
+    *found = slots.size();
     return nullptr;
 }
 

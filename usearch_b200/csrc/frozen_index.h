@@ -9,6 +9,7 @@
 
 #include <cstddef>
 #include <cstdint>
+#include <condition_variable>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -26,8 +27,12 @@ bool search_is_staged(device_index_t const& ix);
 int search_stage_slots(device_index_t const& ix);
 int search_lanes_per_vector(device_index_t const& ix);
 uint32_t search_stage_pad(device_index_t const& ix);
+int search_max_warps_per_sm(device_index_t const& ix);
+bool search_single_stage_set(device_index_t const& ix);
 bool search_needs_norms(uint32_t metric, uint32_t scalar);
 cudaError_t search_compute_norms(device_index_t const& ix, float* norms, cudaStream_t stream);
+cudaError_t search_fill_empty(uint64_t* keys, float* dists, uint32_t* counts, uint32_t* computed, uint32_t* visited, size_t nq,
+                              size_t k, cudaStream_t stream);
 cudaError_t search_build_allow_bits(device_index_t const& ix, uint64_t const* allowed_sorted, uint32_t m, uint32_t* bits,
                                     cudaStream_t stream);
 
@@ -93,6 +98,79 @@ template <typename T> struct pinned_buffer_t {
     }
 };
 
+/* key -> slot(s): open addressing over the host copy of the keys, built on first use. Plays the role of
+ * index_dense_gt::slot_lookup_ (index_dense.hpp:462-500); a `multi` index keeps one entry per (key, slot). */
+struct key_map_t {
+    std::vector<uint32_t> cells; /* slot, or EMPTY_SLOT / TOMB */
+    std::vector<uint64_t> const* keys = nullptr;
+    size_t used = 0;
+    bool built = false;
+    static constexpr uint32_t TOMB = 0xFFFFFFFEu;
+    static size_t hash(uint64_t k) {
+        k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+        return (size_t)k;
+    }
+    void clear() { cells.clear(); used = 0; built = false; }
+    void rebuild(std::vector<uint64_t> const& host_keys, uint64_t free_key, size_t expect) {
+        keys = &host_keys;
+        size_t cap = 64;
+        while (cap < 2 * std::max(expect, host_keys.size()) + 2) cap <<= 1;
+        cells.assign(cap, EMPTY_SLOT);
+        used = 0;
+        built = true;
+        for (size_t s = 0; s < host_keys.size(); ++s)
+            if (host_keys[s] != free_key) insert(host_keys[s], (uint32_t)s);
+    }
+    void insert(uint64_t key, uint32_t slot) { /* keys->at(slot) == key must already hold */
+        if ((used + 1) * 2 > cells.size()) { /* grow: re-insert the live cells */
+            std::vector<uint32_t> old;
+            old.swap(cells);
+            cells.assign(old.size() * 2, EMPTY_SLOT);
+            used = 0;
+            for (uint32_t c : old)
+                if (c != EMPTY_SLOT && c != TOMB) insert((*keys)[c], c);
+        }
+        size_t const mask = cells.size() - 1;
+        size_t h = hash(key) & mask;
+        while (cells[h] != EMPTY_SLOT && cells[h] != TOMB) h = (h + 1) & mask;
+        cells[h] = slot;
+        used += 1;
+    }
+    template <class F> void for_each(uint64_t key, F&& f) const { /* f(slot, cell index) -> bool keep going */
+        if (cells.empty()) return;
+        size_t const mask = cells.size() - 1;
+        for (size_t h = hash(key) & mask; cells[h] != EMPTY_SLOT; h = (h + 1) & mask)
+            if (cells[h] != TOMB && (*keys)[cells[h]] == key)
+                if (!f(cells[h], h)) return;
+    }
+    bool contains(uint64_t key) const {
+        bool hit = false;
+        for_each(key, [&](uint32_t, size_t) { hit = true; return false; });
+        return hit;
+    }
+    size_t count(uint64_t key) const {
+        size_t n = 0;
+        for_each(key, [&](uint32_t, size_t) { ++n; return true; });
+        return n;
+    }
+    void erase_cell(size_t h) { cells[h] = TOMB; }
+};
+
+/* device scratch of the batched builder (builder.cu) */
+struct build_scratch_t {
+    device_buffer_t<uint32_t> task_slot, cand_slots, cand_counts, pair_idx, pair_idx_sorted, heads, counters;
+    device_buffer_t<uint8_t> task_level, sort_temp;
+    device_buffer_t<float> cand_dists, pair_dists;
+    device_buffer_t<uint64_t> pair_keys, pair_keys_sorted;
+    size_t iota_count = 0;
+    void release() {
+        task_slot.release(); cand_slots.release(); cand_counts.release(); pair_idx.release(); pair_idx_sorted.release();
+        heads.release(); counters.release(); task_level.release(); sort_temp.release(); cand_dists.release();
+        pair_dists.release(); pair_keys.release(); pair_keys_sorted.release();
+        iota_count = 0;
+    }
+};
+
 struct frozen_index_t {
     /* configuration (usearch_init_options_t) */
     uint32_t metric = 0, scalar = 0; /* reference char codes */
@@ -103,7 +181,14 @@ struct frozen_index_t {
 
     /* population */
     size_t size = 0, count_deleted = 0;
-    std::vector<int16_t> levels; /* kept on the host: only needed to re-serialise */
+    std::vector<int16_t> levels;     /* kept on the host: re-serialisation and the builder's work lists */
+    std::vector<uint64_t> host_keys; /* host copy of `keys` (slot -> key): lookups by key never touch the device */
+    key_map_t key_map;
+    size_t capacity = 0;                      /* slots the HBM arrays have room for */
+    size_t upper_capacity = 0, upper_rows = 0; /* rows of `upper`: allocated / in use */
+    uint64_t level_seed = 0;
+    bool configured() const { return metric && scalar && dimensions && connectivity; }
+    void build_key_map() { if (!key_map.built) key_map.rebuild(host_keys, free_key, capacity); }
 
     /* device */
     int device = 0;
@@ -146,10 +231,36 @@ struct frozen_index_t {
     size_t serialized_length() const;
     char const* save_blob(uint8_t* out, size_t length) const;
 
+    /* mutation (builder.cu): GPU-assisted add, capacity, tombstones */
+    build_scratch_t build;
+    device_buffer_t<uint8_t> cast_stage; /* raw caller rows awaiting a scalar cast on the device */
+    char const* reserve_slots(size_t slots);
+    char const* reserve_upper_rows(size_t rows);
+    int16_t draw_level(size_t slot) const;
+    char const* add_many(uint64_t const* keys, void const* vectors, size_t count, size_t stride, uint32_t scalar_kind, bool on_device);
+    char const* link_batch(size_t first, size_t count);
+    char const* remove_key(uint64_t key, size_t* removed);
+    char const* rename_key(uint64_t from, uint64_t to, size_t* renamed);
+    char const* get_vectors(uint64_t key, size_t max_count, void* out, uint32_t out_scalar, size_t* found);
+
     /* searches */
-    char const* plan(uint32_t k, uint32_t visited_cap_override, launch_plan_t& plan) const;
+    char const* plan(uint32_t k, uint32_t visited_cap_override, launch_plan_t& plan, uint32_t ef_override = 0) const;
+    char const* prepare_launch(launch_plan_t const& pl, size_t warps, search_args_t& a, cudaStream_t s);
     char const* search_device(void const* d_queries, size_t nq, size_t stride, size_t k, uint64_t* d_keys, float* d_dists,
                               uint32_t* d_counts, uint32_t* d_computed, uint32_t* d_cycles, cudaStream_t stream);
+    /* usearch_search from many host threads: callers that arrive while a launch is in flight are gathered and served by
+     * ONE launch (a leader runs the batch, the others wait for their rows) — the reference serves them from distinct
+     * thread contexts in parallel (index.hpp:3033-3039, index_dense.hpp:1984-2000) */
+    struct single_request_t {
+        void const* query; uint32_t scalar; size_t count; uint64_t* keys; float* dists; size_t found; char const* error; bool done;
+    };
+    std::mutex gather_mutex;
+    std::condition_variable gather_cv;
+    std::vector<single_request_t*> gather_queue;
+    bool gather_leader = false;
+    uint64_t gathered_batches = 0, gathered_queries = 0;
+    char const* search_single(void const* query, uint32_t query_scalar, size_t count, uint64_t* keys, float* dists, size_t* found);
+    char const* upload_queries(void const* queries, size_t nq, size_t stride, uint32_t query_scalar);
     device_buffer_t<uint8_t> exact_scratch;
     char const* exact_host(void const* queries, size_t nq, size_t stride, uint32_t query_scalar, size_t k, uint64_t* keys,
                            float* dists, size_t* counts);
@@ -166,6 +277,14 @@ char const* exact_search_device(device_index_t const& ix, int sm_count, void con
 char const* exact_search_free(void const* dataset, size_t dataset_count, size_t dataset_stride, void const* queries,
                               size_t queries_count, size_t queries_stride, uint32_t scalar, size_t dimensions, uint32_t metric,
                               size_t count, uint64_t* keys, size_t keys_stride, float* distances, size_t distances_stride);
+
+/* builder.cu: scalar casts and single-pair distances on the device */
+char const* cast_rows_device(uint8_t const* src, size_t src_stride, uint32_t from, uint8_t* dst, size_t dst_stride, uint32_t to,
+                             size_t dims, size_t rows, cudaStream_t stream);
+char const* pair_distance_device(device_index_t const& shape, uint8_t const* d_a, uint8_t const* d_b, float* d_out, cudaStream_t stream);
+
+char const* pair_distance_host(void const* a, void const* b, uint32_t scalar, size_t dimensions, uint32_t metric, float* result);
+int default_device(); /* USEARCH_B200_DEVICE, else LOCAL_RANK (one process per GPU under torchrun), else 0 */
 
 /* host-side query casts (index_plugins.hpp:1105-1224) */
 char const* cast_queries(uint32_t from_scalar, uint32_t to_scalar, size_t dims, uint8_t const* src, size_t src_stride, size_t nq,

@@ -375,6 +375,10 @@ __device__ __forceinline__ void measure_staged(device_index_t const& ix, search_
 template <class M, bool STAGED>
 __device__ __forceinline__ void measure_list(device_index_t const& ix, search_args_t const& a, warp_ctx_t& w,
                                              typename M::qconst_t qc, uint32_t ncand, int lane) {
+    /* An empty list (the only member of the top level has one) must not touch the mbarriers: an `expect_tx` of zero bytes
+     * completes a phase that no wait consumes, and every later wait of this warp is then one phase behind — it returns
+     * before its copy has landed, or deadlocks (the round-1 golden-test hang: cluster(level = top) on a one-member top). */
+    if (ncand == 0) return;
     float n0 = 0.f, n1 = 0.f;
     if constexpr (M::NORMS) { /* requested now, consumed after the last pass */
         if ((uint32_t)lane < ncand) n0 = __ldg(ix.norms + w.cand_s[lane]);
@@ -400,10 +404,20 @@ __device__ __forceinline__ bool slot_allowed(device_index_t const& ix, search_ar
 
 /* ---- one query ------------------------------------------------------------------------------ */
 
-template <class M, bool STAGED>
-__device__ __forceinline__ void search_one(device_index_t const& ix, search_args_t const& a, uint32_t qi, warp_ctx_t& w,
-                                           heap_t const& heap, uint32_t* visited, int lane) {
+template <class M, bool STAGED, bool INSERT>
+__device__ __forceinline__ void search_one(device_index_t const& ix, search_args_t const& a, uint32_t qi, uint32_t out_row,
+                                           int const bl_arg, warp_ctx_t& w, heap_t const& heap, uint32_t* visited, int lane) {
     uint32_t const k = a.k, ef = a.ef;
+    /* INSERT mode: search_to_insert_ (index.hpp:4010-4079) on level `bl` — no predicate, slots out. A template
+     * parameter, so that the plain search kernels compile to the code they had before the builder existed. */
+    constexpr bool insert = INSERT;
+    int const bl = INSERT ? bl_arg : 0;
+    uint32_t const width = bl == 0 ? ix.m0 : ix.m; /* list capacity on the searched level */
+    auto row_of = [&](uint32_t slot) -> uint32_t const* {
+        if (bl == 0) return ix.nbr0 + (size_t)slot * ix.m0_stride;
+        uint32_t const ub = __ldg(ix.upper_base + slot); /* a member reached on level bl has rows 1..level >= bl */
+        return ix.upper + ((size_t)ub + (uint32_t)(bl - 1)) * ix.m_stride;
+    };
     uint32_t top_size = 0, heap_size = 0, computed = 0, cycles = 0, status = STATUS_OK;
     uint32_t visited_total = 0;
     bool log_overflow_out = false;
@@ -467,7 +481,7 @@ __device__ __forceinline__ void search_one(device_index_t const& ix, search_args
         float closest_d = cand_d[0];
         __syncwarp();
         bool const cluster = a.cluster_end_level >= 0; /* index_gt::cluster (index.hpp:3092-3125): descent only */
-        int const end_level = cluster ? a.cluster_end_level : 0;
+        int const end_level = cluster ? a.cluster_end_level : bl;
         for (int level = ix.max_level; level > end_level; --level) {
             bool changed;
             do {
@@ -532,7 +546,7 @@ __device__ __forceinline__ void search_one(device_index_t const& ix, search_args
         PHASE(pc0)
         {
             /* cluster(): the closest member at that level is the whole answer, predicate ignored (index.hpp:3122) */
-            bool allowed = cluster || slot_allowed(ix, a, closest);
+            bool allowed = cluster || insert || slot_allowed(ix, a, closest);
             if (allowed) {
                 if (topreg) {
                     if (lane == 0) { rtd[0] = radius; rts[0] = closest; }
@@ -546,14 +560,14 @@ __device__ __forceinline__ void search_one(device_index_t const& ix, search_args
             cand_t cur = heap.root();
             if (cur.d > radius && top_size == ef) break;
             /* the neighbour row is addressed by the root alone: fetch it while lane 0 sifts the heap */
-            uint32_t const* row = ix.nbr0 + (size_t)cur.s * ix.m0_stride;
+            uint32_t const* row = row_of(cur.s);
             uint32_t s0, s1;
             if (cur.s == pre_node) { /* the row was prefetched during the previous hop */
                 s0 = pre_s0;
                 s1 = pre_s1;
             } else {
-                s0 = lane < (int)ix.m0 ? __ldg(row + lane) : EMPTY_SLOT;
-                s1 = lane + 32 < (int)ix.m0 ? __ldg(row + lane + 32) : EMPTY_SLOT;
+                s0 = lane < (int)width ? __ldg(row + lane) : EMPTY_SLOT;
+                s1 = lane + 32 < (int)width ? __ldg(row + lane + 32) : EMPTY_SLOT;
             }
             __syncwarp(); /* every lane holds `cur` before lane 0 rearranges the heap */
             /* BITMAP visits: one atomicOr per neighbour, all in flight together (the frozen lists hold no
@@ -574,9 +588,9 @@ __device__ __forceinline__ void search_one(device_index_t const& ix, search_args
              * Its neighbour row is requested now and only consumed one hop later. */
             if (heap_size) {
                 pre_node = heap.root().s;
-                uint32_t const* next_row = ix.nbr0 + (size_t)pre_node * ix.m0_stride;
-                pre_s0 = lane < (int)ix.m0 ? __ldg(next_row + lane) : EMPTY_SLOT;
-                pre_s1 = lane + 32 < (int)ix.m0 ? __ldg(next_row + lane + 32) : EMPTY_SLOT;
+                uint32_t const* next_row = row_of(pre_node);
+                pre_s0 = lane < (int)width ? __ldg(next_row + lane) : EMPTY_SLOT;
+                pre_s1 = lane + 32 < (int)width ? __ldg(next_row + lane + 32) : EMPTY_SLOT;
             } else
                 pre_node = EMPTY_SLOT;
             PHASE(pc1)
@@ -593,15 +607,15 @@ __device__ __forceinline__ void search_one(device_index_t const& ix, search_args
                 if (f1) cand_s[ncand + __popc(bal1 & lt)] = s1;
                 ncand += __popc(bal1);
                 if (logged) { /* remember which bits this query set */
-                    if (visited_count + ix.m0 > a.visit_log_cap) log_overflow = true;
+                    if (visited_count + width > a.visit_log_cap) log_overflow = true;
                     if (!log_overflow) {
                         if (f0) vlog[visited_count + __popc(bal0 & lt)] = s0;
                         if (f1) vlog[visited_count + __popc(bal0) + __popc(bal1 & lt)] = s1;
                     }
                 }
-                for (uint32_t b = 64; b < ix.m0; b += 32) {
+                for (uint32_t b = 64; b < width; b += 32) {
                     uint32_t i = b + lane;
-                    uint32_t s = i < ix.m0 ? __ldg(row + i) : EMPTY_SLOT;
+                    uint32_t s = i < width ? __ldg(row + i) : EMPTY_SLOT;
                     uint32_t o = s != EMPTY_SLOT ? atomicOr(&visited[s >> 5], 1u << (s & 31)) : 0xFFFFFFFFu;
                     bool f = s != EMPTY_SLOT && !((o >> (s & 31)) & 1u);
                     uint32_t bal = __ballot_sync(0xffffffffu, f);
@@ -611,10 +625,10 @@ __device__ __forceinline__ void search_one(device_index_t const& ix, search_args
                 }
             } else {
                 /* visits.reserve(): keep the table at most half full so probing terminates quickly */
-                if ((visited_count + ix.m0) * 2 > a.visited_cap) { status = STATUS_VISITED_OVERFLOW; break; }
-                for (uint32_t b = 0; b < ix.m0; b += 32) {
+                if ((visited_count + width) * 2 > a.visited_cap) { status = STATUS_VISITED_OVERFLOW; break; }
+                for (uint32_t b = 0; b < width; b += 32) {
                     uint32_t i = b + lane;
-                    uint32_t s = b == 0 ? s0 : (b == 32 ? s1 : (i < ix.m0 ? __ldg(row + i) : EMPTY_SLOT));
+                    uint32_t s = b == 0 ? s0 : (b == 32 ? s1 : (i < width ? __ldg(row + i) : EMPTY_SLOT));
                     bool fresh = false;
                     if (s != EMPTY_SLOT) {
                         uint32_t h = hash_slot(s) & vmask;
@@ -656,7 +670,7 @@ __device__ __forceinline__ void search_one(device_index_t const& ix, search_args
                         heap.push(heap_size, cand_t{d, s}, lane);
                         heap_size += 1;
                         if (prof) { n_push += 1; max_heap = max(max_heap, heap_size); }
-                        bool allowed = slot_allowed(ix, a, s);
+                        bool allowed = insert || slot_allowed(ix, a, s);
                         if (allowed) {
                             if (topreg) {
                                 top_insert_reg(rtd, rts, top_size, ef, d, s, lane);
@@ -702,11 +716,12 @@ __device__ __forceinline__ void search_one(device_index_t const& ix, search_args
                 uint64_t key = 0;
                 uint32_t bits = SNAN_BITS;
                 if (i < count) {
-                    key = ix.keys[rts[j]];
+                    key = insert ? (uint64_t)rts[j] : ix.keys[rts[j]];
                     bits = __float_as_uint(rtd[j]);
                 }
-                a.out_keys[(size_t)qi * k + i] = key;
-                reinterpret_cast<uint32_t*>(a.out_dists)[(size_t)qi * k + i] = bits;
+                if (insert) a.out_slots[(size_t)out_row * k + i] = (uint32_t)key;
+                else a.out_keys[(size_t)out_row * k + i] = key;
+                reinterpret_cast<uint32_t*>(a.out_dists)[(size_t)out_row * k + i] = bits;
             }
         }
     } else {
@@ -714,18 +729,19 @@ __device__ __forceinline__ void search_one(device_index_t const& ix, search_args
             uint64_t key = 0;
             uint32_t bits = SNAN_BITS;
             if (i < count) {
-                key = ix.keys[top_s[i]];
+                key = insert ? (uint64_t)top_s[i] : ix.keys[top_s[i]];
                 bits = __float_as_uint(top_d[i]);
             }
-            a.out_keys[(size_t)qi * k + i] = key;
-            reinterpret_cast<uint32_t*>(a.out_dists)[(size_t)qi * k + i] = bits;
+            if (insert) a.out_slots[(size_t)out_row * k + i] = (uint32_t)key;
+            else a.out_keys[(size_t)out_row * k + i] = key;
+            reinterpret_cast<uint32_t*>(a.out_dists)[(size_t)out_row * k + i] = bits;
         }
     }
     if (lane == 0) {
-        a.out_counts[qi] = count;
-        if (a.out_computed) a.out_computed[qi] = computed;
-        if (a.out_visited) a.out_visited[qi] = cycles;
-        a.status[qi] = status;
+        a.out_counts[out_row] = count;
+        if (a.out_computed) a.out_computed[out_row] = computed;
+        if (a.out_visited) a.out_visited[out_row] = cycles;
+        a.status[out_row] = status;
     }
     __syncwarp();
     if (prof && lane == 0) {
@@ -745,11 +761,9 @@ __device__ __forceinline__ void search_one(device_index_t const& ix, search_args
 #undef PHASE
 }
 
-/* MIN_CTAS: resident CTAs per SM the register allocation must allow. 8 for the staged kernel, 16 for the direct one;
- * EXPERIMENTAL (USEARCH_B200_STAGED_DENSE=1, not yet run on hardware): the staged kernel at 16 (<= 128 registers, no
- * spills) for vectors of 1-1.5 KB - i8, f16/bf16 with the WORD metrics - where a hop moves few bytes and the fixed
- * per-hop latency needs more warps to hide. */
-template <class M, bool STAGED, int MIN_CTAS = (STAGED ? 8 : 16)>
+/* MIN_CTAS: resident CTAs (= warps) per SM the register allocation must allow: 8 for the staged f32 kernel (its 16
+ * accumulators and the register-resident `top` want ~220 registers), 16 for everything else (see the dispatch below). */
+template <class M, bool STAGED, int MIN_CTAS = (STAGED ? 8 : 16), bool INSERT = false>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS) hnsw_search_kernel(__grid_constant__ device_index_t const ix,
                                                               __grid_constant__ search_args_t const a) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -777,9 +791,33 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) hnsw_search_kernel(__grid_c
         if (lane == 0) item = atomicAdd(a.work_counter, 1u);
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= a.nq) break;
-        uint32_t qi = a.query_list ? a.query_list[item] : item;
-        search_one<M, STAGED>(ix, a, qi, w, heap, visited, lane);
+        uint32_t const qi = a.query_list ? a.query_list[item] : item;
+        /* INSERT mode: one output row per work item (the same member is searched once per level) */
+        uint32_t const out_row = INSERT ? item : qi;
+        int const bl = INSERT ? (int)a.task_levels[item] : 0;
+        search_one<M, STAGED, INSERT>(ix, a, qi, out_row, bl, w, heap, visited, lane);
     }
+}
+
+/* ---- results of a search in an empty index: no matches, rows padded like dump_to (index.hpp:2715-2720) ------------- */
+
+__global__ void fill_empty_kernel(uint64_t* keys, uint32_t* dist_bits, uint32_t* counts, uint32_t* computed, uint32_t* visited,
+                                  size_t nq, size_t k) {
+    size_t const i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nq * k) { keys[i] = 0; dist_bits[i] = SNAN_BITS; }
+    if (i < nq) {
+        counts[i] = 0;
+        if (computed) computed[i] = 0;
+        if (visited) visited[i] = 0;
+    }
+}
+
+cudaError_t search_fill_empty(uint64_t* keys, float* dists, uint32_t* counts, uint32_t* computed, uint32_t* visited, size_t nq,
+                              size_t k, cudaStream_t stream) {
+    size_t const total = nq * (k ? k : 1);
+    fill_empty_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(keys, reinterpret_cast<uint32_t*>(dists), counts, computed,
+                                                                           visited, nq, k);
+    return cudaGetLastError();
 }
 
 /* ---- filtered search: allowed keys -> bitmap over slots -------------------------------------------- */
@@ -840,121 +878,100 @@ cudaError_t search_compute_norms(device_index_t const& ix, float* norms, cudaStr
 
 /* ---- host-side dispatch --------------------------------------------------------------------- */
 
-template <class M, bool STAGED>
-static cudaError_t launch_t(device_index_t const& ix, search_args_t const& a, int blocks, size_t smem, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(hnsw_search_kernel<M, STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+/*
+ *  Which kernel serves which index (measured on B200, profiles/r02_variants.md):
+ *    f32, vectors >= 256 B      STAGED, 4 lanes per vector, 8 resident warps per SM allowed by the register budget
+ *    f16 / bf16, >= 256 B       STAGED with the WORD metrics (4 lanes per vector split by accumulator) compiled for 16
+ *                               resident warps per SM; one stage set up to 2 KB vectors (1M x 768 f16, ef 256: 0.40 ->
+ *                               0.61 of the HBM peak against one lane per vector in a single 32-slot set)
+ *    i8, >= 256 B               STAGED compiled for 16 resident warps per SM, one stage set up to 2 KB (1M x 1024 i8:
+ *                               0.53 -> 0.64): a hop moves few bytes, so resident warps matter more than double buffering
+ *    b1, and anything < 256 B   DIRECT (16-byte chunks through registers)
+ *  Every one of them also exists as an INSERT-mode kernel for the builder.
+ */
+template <class M, bool STAGED, int MIN_CTAS>
+static cudaError_t launch_k(device_index_t const& ix, search_args_t const& a, int blocks, size_t smem, cudaStream_t stream) {
+    if (a.out_slots) { /* INSERT mode (builder.cu) */
+        auto kernel = hnsw_search_kernel<M, STAGED, MIN_CTAS, true>;
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kernel<<<blocks, THREADS, smem, stream>>>(ix, a);
+        return cudaGetLastError();
+    }
+    auto kernel = hnsw_search_kernel<M, STAGED, MIN_CTAS, false>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    hnsw_search_kernel<M, STAGED><<<blocks, THREADS, smem, stream>>>(ix, a);
+    kernel<<<blocks, THREADS, smem, stream>>>(ix, a);
     return cudaGetLastError();
 }
 
-template <class M, bool STAGED> static cudaError_t occupancy_t(int* blocks_per_sm, size_t smem) {
-    cudaError_t e = cudaFuncSetAttribute(hnsw_search_kernel<M, STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <class M, bool STAGED, int MIN_CTAS> static cudaError_t occupancy_k(int* blocks_per_sm, size_t smem) {
+    auto kernel = hnsw_search_kernel<M, STAGED, MIN_CTAS, false>; /* the INSERT twin needs no more registers */
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, hnsw_search_kernel<M, STAGED>, THREADS, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kernel, THREADS, smem);
 }
 
-bool half_words_enabled();
-
-template <class M> static cudaError_t launch_dense_t(device_index_t const& ix, search_args_t const& a, int blocks, size_t smem, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(hnsw_search_kernel<M, true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    hnsw_search_kernel<M, true, 16><<<blocks, THREADS, smem, stream>>>(ix, a);
-    return cudaGetLastError();
-}
-template <class M> static cudaError_t occupancy_dense_t(int* blocks_per_sm, size_t smem) {
-    cudaError_t e = cudaFuncSetAttribute(hnsw_search_kernel<M, true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, hnsw_search_kernel<M, true, 16>, THREADS, smem);
-}
-static bool staged_dense_enabled() {
-    static bool const on = [] { char const* v = std::getenv("USEARCH_B200_STAGED_DENSE"); return v && std::atoi(v) == 1; }();
-    return on;
-}
-
-#define DISPATCH_M(FN, M, ...) return staged ? FN<M, true>(__VA_ARGS__) : FN<M, false>(__VA_ARGS__)
-/* half precision: the WORD variant (4 lanes per vector, by accumulator) on the staged path when enabled */
-#define DISPATCH_H(FN, M, MW, ...) \
-    return staged ? (half_words_enabled() ? FN<MW, true>(__VA_ARGS__) : FN<M, true>(__VA_ARGS__)) : FN<M, false>(__VA_ARGS__)
-#define DISPATCH(FN, ...)                                                                                  \
-    switch (ix.scalar) {                                                                                   \
-    case SCALAR_F32:                                                                                       \
-        if (ix.metric == METRIC_L2SQ) DISPATCH_M(FN, l2sq_f32_t, __VA_ARGS__);                             \
-        if (ix.metric == METRIC_IP) DISPATCH_M(FN, ip_f32_t, __VA_ARGS__);                                 \
-        if (ix.metric == METRIC_COS) DISPATCH_M(FN, cos_f32_t, __VA_ARGS__);                               \
-        break;                                                                                             \
-    case SCALAR_F16:                                                                                       \
-        if (ix.metric == METRIC_L2SQ) DISPATCH_H(FN, l2sq_half_t<f16_conv_t>, l2sq_halfw_t<f16_conv_t>, __VA_ARGS__);                \
-        if (ix.metric == METRIC_IP) DISPATCH_H(FN, ip_half_t<f16_conv_t>, ip_halfw_t<f16_conv_t>, __VA_ARGS__);                    \
-        if (ix.metric == METRIC_COS) DISPATCH_H(FN, cos_half_t<f16_conv_t>, cos_halfw_t<f16_conv_t>, __VA_ARGS__);                  \
-        break;                                                                                             \
-    case SCALAR_BF16:                                                                                      \
-        if (ix.metric == METRIC_L2SQ) DISPATCH_H(FN, l2sq_half_t<bf16_conv_t>, l2sq_halfw_t<bf16_conv_t>, __VA_ARGS__);               \
-        if (ix.metric == METRIC_IP) DISPATCH_H(FN, ip_half_t<bf16_conv_t>, ip_halfw_t<bf16_conv_t>, __VA_ARGS__);                   \
-        if (ix.metric == METRIC_COS) DISPATCH_H(FN, cos_half_t<bf16_conv_t>, cos_halfw_t<bf16_conv_t>, __VA_ARGS__);                 \
-        break;                                                                                             \
-    case SCALAR_I8:                                                                                        \
-        if (ix.metric == METRIC_L2SQ) DISPATCH_M(FN, l2sq_i8_t<4>, __VA_ARGS__);                           \
-        if (ix.metric == METRIC_IP) DISPATCH_M(FN, ip_i8_t<4>, __VA_ARGS__);                               \
-        if (ix.metric == METRIC_COS) DISPATCH_M(FN, cos_i8_t<4>, __VA_ARGS__);                             \
-        break;                                                                                             \
-    case SCALAR_B1:                                                                                        \
-        if (ix.metric == METRIC_HAMMING) return FN<hamming_b1_t<2>, false>(__VA_ARGS__);                   \
-        if (ix.metric == METRIC_TANIMOTO || ix.metric == METRIC_JACCARD) return FN<tanimoto_b1_t<2>, false>(__VA_ARGS__); \
-        if (ix.metric == METRIC_SORENSEN) return FN<sorensen_b1_t<2>, false>(__VA_ARGS__);                 \
-        break;                                                                                             \
-    default: break;                                                                                        \
-    }                                                                                                      \
+/* OP is `launch_k` or `occupancy_k`; ARGS its run-time arguments in parentheses */
+#define FOR_METRIC(OP, ARGS)                                                                                    \
+    switch (ix.scalar) {                                                                                        \
+    case SCALAR_F32:                                                                                            \
+        if (ix.metric == METRIC_L2SQ) return staged ? OP<l2sq_f32_t, true, 8> ARGS : OP<l2sq_f32_t, false, 16> ARGS; \
+        if (ix.metric == METRIC_IP) return staged ? OP<ip_f32_t, true, 8> ARGS : OP<ip_f32_t, false, 16> ARGS;  \
+        if (ix.metric == METRIC_COS) return staged ? OP<cos_f32_t, true, 8> ARGS : OP<cos_f32_t, false, 16> ARGS; \
+        break;                                                                                                  \
+    case SCALAR_F16:                                                                                            \
+        if (ix.metric == METRIC_L2SQ) return staged ? OP<l2sq_halfw_t<f16_conv_t>, true, 16> ARGS : OP<l2sq_half_t<f16_conv_t>, false, 16> ARGS; \
+        if (ix.metric == METRIC_IP) return staged ? OP<ip_halfw_t<f16_conv_t>, true, 16> ARGS : OP<ip_half_t<f16_conv_t>, false, 16> ARGS; \
+        if (ix.metric == METRIC_COS) return staged ? OP<cos_halfw_t<f16_conv_t>, true, 16> ARGS : OP<cos_half_t<f16_conv_t>, false, 16> ARGS; \
+        break;                                                                                                  \
+    case SCALAR_BF16:                                                                                           \
+        if (ix.metric == METRIC_L2SQ) return staged ? OP<l2sq_halfw_t<bf16_conv_t>, true, 16> ARGS : OP<l2sq_half_t<bf16_conv_t>, false, 16> ARGS; \
+        if (ix.metric == METRIC_IP) return staged ? OP<ip_halfw_t<bf16_conv_t>, true, 16> ARGS : OP<ip_half_t<bf16_conv_t>, false, 16> ARGS; \
+        if (ix.metric == METRIC_COS) return staged ? OP<cos_halfw_t<bf16_conv_t>, true, 16> ARGS : OP<cos_half_t<bf16_conv_t>, false, 16> ARGS; \
+        break;                                                                                                  \
+    case SCALAR_I8:                                                                                             \
+        if (ix.metric == METRIC_L2SQ) return staged ? OP<l2sq_i8_t<4>, true, 16> ARGS : OP<l2sq_i8_t<4>, false, 16> ARGS; \
+        if (ix.metric == METRIC_IP) return staged ? OP<ip_i8_t<4>, true, 16> ARGS : OP<ip_i8_t<4>, false, 16> ARGS; \
+        if (ix.metric == METRIC_COS) return staged ? OP<cos_i8_t<4>, true, 16> ARGS : OP<cos_i8_t<4>, false, 16> ARGS; \
+        break;                                                                                                  \
+    case SCALAR_B1:                                                                                             \
+        if (ix.metric == METRIC_HAMMING) return OP<hamming_b1_t<2>, false, 16> ARGS;                            \
+        if (ix.metric == METRIC_TANIMOTO || ix.metric == METRIC_JACCARD) return OP<tanimoto_b1_t<2>, false, 16> ARGS; \
+        if (ix.metric == METRIC_SORENSEN) return OP<sorensen_b1_t<2>, false, 16> ARGS;                          \
+        break;                                                                                                  \
+    default: break;                                                                                             \
+    }                                                                                                           \
     return cudaErrorInvalidValue;
 
 /* vectors of at least this many bytes are fetched with TMA bulk copies into shared memory */
 constexpr uint32_t STAGED_MIN_BYTES = 256;
 
 bool search_is_staged(device_index_t const& ix) { return ix.scalar != SCALAR_B1 && ix.vec_stride >= STAGED_MIN_BYTES; }
-/* EXPERIMENTAL (not yet validated on hardware, off by default): USEARCH_B200_HALF_WORDS=1 */
-bool half_words_enabled() {
-    static bool const on = [] { char const* v = std::getenv("USEARCH_B200_HALF_WORDS"); return v && std::atoi(v) == 1; }();
-    return on;
-}
 static bool is_half(device_index_t const& ix) { return ix.scalar == SCALAR_F16 || ix.scalar == SCALAR_BF16; }
-int search_lanes_per_vector(device_index_t const& ix) {
-    if (!is_half(ix)) return 4;
-    return search_is_staged(ix) && half_words_enabled() ? 4 : 1;
-}
+int search_lanes_per_vector(device_index_t const&) { return 4; } /* every STAGED metric splits a vector over 4 lanes */
 /* bytes added to a 128-byte-rounded slot so that the lane groups of a pass hit disjoint banks: 16*LPV for 16-byte
  * units (each lane of a group reads its own chunk), 16 for word units (a group reads one chunk) */
-uint32_t search_stage_pad(device_index_t const& ix) {
-    return is_half(ix) && search_lanes_per_vector(ix) == 4 ? 16u : 16u * (uint32_t)search_lanes_per_vector(ix);
+uint32_t search_stage_pad(device_index_t const& ix) { return is_half(ix) ? 16u : 64u; }
+int search_stage_slots(device_index_t const& ix) { return search_is_staged(ix) ? 8 : 0; }
+/* kernels compiled for 16 resident warps per SM: what the plan may count on */
+int search_max_warps_per_sm(device_index_t const& ix) {
+    if (!search_is_staged(ix)) return 24;
+    return ix.scalar == SCALAR_F32 ? 8 : 16;
 }
-int search_stage_slots(device_index_t const& ix) { return search_is_staged(ix) ? 32 / search_lanes_per_vector(ix) : 0; }
-
-#define DISPATCH_DENSE(FN, ...)                                                                             \
-    if (staged_dense_enabled() && search_is_staged(ix)) {                                                  \
-        if (ix.scalar == SCALAR_I8) {                                                                      \
-            if (ix.metric == METRIC_L2SQ) return FN<l2sq_i8_t<4>>(__VA_ARGS__);                            \
-            if (ix.metric == METRIC_IP) return FN<ip_i8_t<4>>(__VA_ARGS__);                                \
-            if (ix.metric == METRIC_COS) return FN<cos_i8_t<4>>(__VA_ARGS__);                              \
-        } else if (ix.scalar == SCALAR_F16 && half_words_enabled()) {                                      \
-            if (ix.metric == METRIC_L2SQ) return FN<l2sq_halfw_t<f16_conv_t>>(__VA_ARGS__);                \
-            if (ix.metric == METRIC_IP) return FN<ip_halfw_t<f16_conv_t>>(__VA_ARGS__);                    \
-            if (ix.metric == METRIC_COS) return FN<cos_halfw_t<f16_conv_t>>(__VA_ARGS__);                  \
-        } else if (ix.scalar == SCALAR_BF16 && half_words_enabled()) {                                     \
-            if (ix.metric == METRIC_L2SQ) return FN<l2sq_halfw_t<bf16_conv_t>>(__VA_ARGS__);               \
-            if (ix.metric == METRIC_IP) return FN<ip_halfw_t<bf16_conv_t>>(__VA_ARGS__);                   \
-            if (ix.metric == METRIC_COS) return FN<cos_halfw_t<bf16_conv_t>>(__VA_ARGS__);                 \
-        }                                                                                                  \
-    }
+/* one stage set (no double buffering, more resident warps) for the short staged vectors of the 16-warp kernels */
+bool search_single_stage_set(device_index_t const& ix) {
+    return search_is_staged(ix) && ix.scalar != SCALAR_F32 && ix.vec_stride <= 2048;
+}
 
 cudaError_t search_launch(device_index_t const& ix, search_args_t const& a, int blocks, size_t smem, cudaStream_t stream) {
     bool const staged = search_is_staged(ix);
-    DISPATCH_DENSE(launch_dense_t, ix, a, blocks, smem, stream)
-    DISPATCH(launch_t, ix, a, blocks, smem, stream)
+    FOR_METRIC(launch_k, (ix, a, blocks, smem, stream))
 }
 
 cudaError_t search_occupancy(device_index_t const& ix, int* blocks_per_sm, size_t smem) {
     bool const staged = search_is_staged(ix);
-    DISPATCH_DENSE(occupancy_dense_t, blocks_per_sm, smem)
-    DISPATCH(occupancy_t, blocks_per_sm, smem)
+    FOR_METRIC(occupancy_k, (blocks_per_sm, smem))
 }
 
 bool search_supported(uint32_t metric, uint32_t scalar) {

@@ -50,7 +50,7 @@ EXPORTED_SYMBOLS = [
     "usearch_search_many", "usearch_b200_search_many_device", "usearch_b200_search_many_stats",
     "usearch_b200_filtered_search_many", "usearch_b200_exact_search_many", "usearch_b200_cluster_many",
     "usearch_b200_profile_phases", "usearch_b200_device", "usearch_b200_kernel_launches", "usearch_b200_last_kernel_ms",
-    "usearch_b200_bytes_per_vector", "usearch_b200_max_level",
+    "usearch_b200_bytes_per_vector", "usearch_b200_max_level", "usearch_b200_add_many", "usearch_b200_add_many_device",
 ]
 
 
@@ -119,6 +119,22 @@ def load_library() -> C.CDLL:
     lib.usearch_b200_bytes_per_vector.argtypes = [C.c_void_p]
     lib.usearch_b200_max_level.restype = C.c_size_t
     lib.usearch_b200_max_level.argtypes = [C.c_void_p]
+    lib.usearch_reserve.argtypes = [C.c_void_p, C.c_size_t, err]
+    for name in ("usearch_b200_add_many", "usearch_b200_add_many_device"):
+        getattr(lib, name).restype = None
+        getattr(lib, name).argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, err]
+    lib.usearch_contains.restype = C.c_bool
+    lib.usearch_contains.argtypes = [C.c_void_p, C.c_uint64, err]
+    lib.usearch_count.restype = C.c_size_t
+    lib.usearch_count.argtypes = [C.c_void_p, C.c_uint64, err]
+    lib.usearch_get.restype = C.c_size_t
+    lib.usearch_get.argtypes = [C.c_void_p, C.c_uint64, C.c_size_t, C.c_void_p, C.c_int, err]
+    lib.usearch_remove.restype = C.c_size_t
+    lib.usearch_remove.argtypes = [C.c_void_p, C.c_uint64, err]
+    lib.usearch_rename.restype = C.c_size_t
+    lib.usearch_rename.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, err]
+    lib.usearch_distance.restype = C.c_float
+    lib.usearch_distance.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_int, err]
     _lib = lib
     return lib
 
@@ -175,10 +191,10 @@ class BatchMatches:
 
 
 class Index:
-    """Search-side drop-in for ``usearch.index.Index`` whose graph lives frozen in B200 HBM.
+    """Drop-in for ``usearch.index.Index`` whose graph lives in B200 HBM.
 
-    Build the graph with the reference (or load a ``.usearch`` file), then ``load``/``view``/``restore``
-    it here; ``search`` runs the whole batch as one persistent-kernel launch.
+    ``add`` links batches of new members into the graph on the GPU; ``load``/``view``/``restore`` take a ``.usearch``
+    file built anywhere; ``search`` runs the whole batch as one persistent-kernel launch.
     """
 
     def __init__(self, *, ndim: int = 0, metric: str = "cos", dtype: str = "f32", connectivity: int = 16,
@@ -282,10 +298,84 @@ class Index:
         self._expansion_search = v
         self._lib.usearch_change_expansion_search(self._h, v, None)
 
-    def add(self, keys, vectors, **_):
+    @property
+    def expansion_add(self) -> int:
+        return self._lib.usearch_expansion_add(self._h, None)
+
+    @expansion_add.setter
+    def expansion_add(self, v: int) -> None:
+        self._lib.usearch_change_expansion_add(self._h, v, None)
+
+    # ---- mutation (index.py:560-700 `add`, :800-900 `remove`/`rename`/`get`/`contains`/`count`) -------------
+    def reserve(self, capacity: int) -> None:
         err = C.c_char_p()
-        self._lib.usearch_add(self._h, 0, None, 0, C.byref(err))
+        self._lib.usearch_reserve(self._h, int(capacity), C.byref(err))
         _raise(err)
+
+    def add(self, keys, vectors: np.ndarray, *, copy: bool = True, threads: int = 0, log=False, progress=None):
+        """`Index.add` (index.py:560-640): one key + vector, or a batch. The batch is linked into the graph on the
+        GPU (builder.cu); `keys=None` numbers the rows from the current size, as the reference does. Returns the keys."""
+        vectors = np.asarray(vectors)
+        if vectors.ndim == 1:
+            vectors = vectors[None, :]
+        if not vectors.flags.c_contiguous and vectors.strides[1] != vectors.itemsize:
+            vectors = np.ascontiguousarray(vectors)
+        n = vectors.shape[0]
+        if keys is None:
+            start = len(self)
+            keys = np.arange(start, start + n, dtype=np.uint64)
+        keys = np.ascontiguousarray(np.atleast_1d(np.asarray(keys)), dtype=np.uint64)
+        if keys.shape[0] != n:
+            raise ValueError("The number of keys must match the number of vectors")
+        kind = self._kind_of(vectors)
+        err = C.c_char_p()
+        self._lib.usearch_b200_add_many(self._h, keys.ctypes.data_as(C.c_void_p), vectors.ctypes.data_as(C.c_void_p), n,
+                                        vectors.strides[0], SCALAR_KIND[kind], C.byref(err))
+        _raise(err)
+        return keys
+
+    def add_device(self, keys_ptr: int, vectors_ptr: int, n: int, stride: int, kind: Optional[str] = None) -> None:
+        """Batch add from DEVICE memory (raw pointers): no host round trip for the vectors."""
+        err = C.c_char_p()
+        self._lib.usearch_b200_add_many_device(self._h, keys_ptr, vectors_ptr, n, stride,
+                                               SCALAR_KIND[kind or self._dtype], C.byref(err))
+        _raise(err)
+
+    def contains(self, key: int) -> bool:
+        return bool(self._lib.usearch_contains(self._h, int(key), None))
+
+    __contains__ = contains
+
+    def count(self, key: int) -> int:
+        return int(self._lib.usearch_count(self._h, int(key), None))
+
+    def get(self, key: int, dtype: Optional[str] = None, count: int = 1) -> Optional[np.ndarray]:
+        """`Index.get` (index.py:820-870): the vector(s) stored under `key`, or None."""
+        kind = dtype or self._dtype
+        np_t = {"f32": np.float32, "f64": np.float64, "f16": np.float16, "bf16": np.uint16, "i8": np.int8, "b1": np.uint8}[kind]
+        cols = (self.ndim + 7) // 8 if kind == "b1" else self.ndim
+        out = np.zeros((count, cols), dtype=np_t)
+        err = C.c_char_p()
+        found = self._lib.usearch_get(self._h, int(key), count, out.ctypes.data_as(C.c_void_p), SCALAR_KIND[kind], C.byref(err))
+        _raise(err)
+        if not found:
+            return None
+        return out[0] if count == 1 else out[:found]
+
+    def remove(self, key: int) -> int:
+        err = C.c_char_p()
+        n = self._lib.usearch_remove(self._h, int(key), C.byref(err))
+        _raise(err)
+        return int(n)
+
+    def rename(self, key_from: int, key_to: int) -> int:
+        err = C.c_char_p()
+        n = self._lib.usearch_rename(self._h, int(key_from), int(key_to), C.byref(err))
+        _raise(err)
+        return int(n)
+
+    def clear(self) -> None:
+        self._lib.usearch_clear(self._h, None)
 
     # ---- search (index.py:700-748) ---------------------------------------------------------------
     def _kind_of(self, vectors: np.ndarray) -> str:
