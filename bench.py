@@ -1,19 +1,21 @@
 #!/usr/bin/env python
 """bench.py — the reference's headline metric (QPS of batched HNSW search at recall@10 >= 0.95) on B200.
 
-One "step" = one batched `search()` over a fresh batch of synthetic queries against the frozen index.
-Default workload = BASELINE.json configs[1]: 1M x 768 f32 cosine, M=32, ef=128, batch 4096, k=10.
+One "step" = one batched `search()` over a fresh batch of synthetic queries against the index in HBM.
+Default workload = the configuration BASELINE.json's metric is quoted on: 10M x 768 f32 cosine (M=32, ef=128,
+batch 4096, k=10). The collection is generated on the GPU and the graph is BUILT on the GPU by the batched builder
+(`usearch_b200_add_many_device`, csrc/builder.cu) in about a minute — the reference needs more than half an hour of
+16-core time for the same graph — and both arms search that same graph.
 
   python bench.py --gpus 1 --steps K --warmup W            # our arm: CUDA path through the C ABI
-  python bench.py --impl reference --steps K --warmup W    # the reference's own CPU search (oracle/_ref)
+  python bench.py --impl reference --steps K --warmup W    # the reference's own CPU search (oracle/_ref) of that graph
+  torchrun ... bench.py --gpus N                           # N > 1: replicas (index fits one GPU) or shards (--parallelism)
 
-Both arms search the SAME serialised graph, built once by the unmodified reference (cached under
-.cache/bench). See DESIGN.md §6 for what each JSON key means and how the roofline figure is derived.
+See DESIGN.md §6 for what each JSON key means and how the roofline figure is derived.
 """
 from __future__ import annotations
 
 import argparse
-import hashlib
 import json
 import os
 import subprocess
@@ -28,8 +30,16 @@ sys.path.insert(0, ROOT)
 
 from usearch_b200 import datagen  # noqa: E402
 
-CACHE = os.environ.get("USEARCH_B200_CACHE", os.path.join(ROOT, ".cache", "bench"))
 METRIC = "QPS @ recall@10>=0.95"
+CHUNK = 262144  # rows generated at a time; chunk c of a collection is a pure function of (seed, c)
+WORKLOADS = {  # BASELINE.json configs + the configuration its metric is quoted on (NS)
+    "NS": dict(n=10_000_000, dim=768, metric="cos", dtype="f32", connectivity=32, ef=128, batch=4096),
+    "C1": dict(n=100_000, dim=128, metric="l2sq", dtype="f32", connectivity=16, ef=64, batch=4096),
+    "C2": dict(n=1_000_000, dim=768, metric="cos", dtype="f32", connectivity=32, ef=128, batch=4096),
+    "C3": dict(n=10_000_000, dim=768, metric="cos", dtype="f16", connectivity=32, ef=256, batch=65536),
+    "C4": dict(n=10_000_000, dim=1024, metric="ip", dtype="i8", connectivity=16, ef=128, batch=16384, parallelism="shard"),
+    "C5": dict(n=100_000_000, dim=256, metric="hamming", dtype="b1", connectivity=64, ef=64, batch=32768, parallelism="shard"),
+}
 
 
 def log(*a):
@@ -54,24 +64,35 @@ def parse_args():
     p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    # workload (defaults = BASELINE.json configs[1]); overridable for development runs only
-    p.add_argument("--n", type=int, default=1_000_000)
-    p.add_argument("--dim", type=int, default=768)
-    p.add_argument("--metric", default="cos")
-    p.add_argument("--dtype", default="f32")
-    p.add_argument("--connectivity", type=int, default=32)
+    p.add_argument("--workload", default="NS", choices=sorted(WORKLOADS), help="a named configuration of BASELINE.json")
+    # overrides of the named workload, for development runs only
+    p.add_argument("--n", type=int)
+    p.add_argument("--dim", type=int)
+    p.add_argument("--metric")
+    p.add_argument("--dtype")
+    p.add_argument("--connectivity", type=int)
+    p.add_argument("--ef", type=int)
+    p.add_argument("--batch", type=int)
     p.add_argument("--expansion-add", type=int, default=128)
-    p.add_argument("--ef", type=int, default=128)
-    p.add_argument("--batch", type=int, default=4096)
     p.add_argument("--k", type=int, default=10)
     p.add_argument("--rank-latent", type=int, default=16)
     p.add_argument("--cpu-sample-seconds", type=float, default=12.0)
     p.add_argument("--no-cpu-baseline", action="store_true")
-    p.add_argument("--parallelism", default="shard", choices=["shard", "replica"],
-                   help="N > 1 only. shard (default, the north-star layout): the collection is split by key, every rank "
-                        "searches every query, one NCCL all-gather + merge. replica: every rank holds the whole index and "
-                        "serves its own batch, no exchange (SURVEY.md 8e: 'replicated index, split batch').")
-    return p.parse_args()
+    p.add_argument("--no-next-rows", action="store_true")
+    p.add_argument("--builder", default="gpu", choices=["gpu", "reference"],
+                   help="who builds the graph both arms search: the GPU builder (default) or the reference on the host cores")
+    p.add_argument("--parallelism", default=None, choices=["replica", "shard"],
+                   help="N > 1 only. replica (default when the index fits one GPU): every rank holds the whole index and serves "
+                        "its own batches, no exchange step. shard (C4/C5: capacity): the collection is split by key, every "
+                        "rank searches every query, ONE NCCL all-gather + merge kernel (csrc/shards.cu).")
+    a = p.parse_args()
+    w = WORKLOADS[a.workload]
+    for key in ("n", "dim", "metric", "dtype", "connectivity", "ef", "batch"):
+        if getattr(a, key) is None:
+            setattr(a, key, w[key])
+    if a.parallelism is None:
+        a.parallelism = w.get("parallelism", "replica")
+    return a
 
 
 def workload_name(a) -> str:
@@ -80,75 +101,138 @@ def workload_name(a) -> str:
 
 
 # ------------------------------------------------------------------------------------------------
-#  data + index (shared by both arms, cached on local disk)
+#  synthetic collection, generated chunk by chunk on the device
 # ------------------------------------------------------------------------------------------------
 
-def shard_key(a, shard: int, shards: int) -> str:
-    desc = f"v1|{a.n}|{a.dim}|{a.metric}|{a.dtype}|{a.connectivity}|{a.expansion_add}|{a.rank_latent}|{shard}|{shards}"
-    return hashlib.sha1(desc.encode()).hexdigest()[:16]
+class Collection:
+    """Rank-r latent Gaussian rows x = z W + 0.1 eps (seeds 42 base / 43 queries / 44 mixing matrix), quantised to the
+    index's scalar kind the way a user would before `add`. Chunk c is a pure function of (seed, c): the builder, the
+    ground truth and the other arm regenerate exactly the same rows without keeping 30 GB around."""
+
+    def __init__(self, a, device):
+        import torch
+        self.a, self.device, self.torch = a, device, torch
+        w = np.random.default_rng(44).standard_normal((a.rank_latent, a.dim)).astype(np.float32)
+        self.w = torch.from_numpy(w).to(device)
+
+    def rows_f32(self, seed: int, chunk: int, rows: int):
+        torch = self.torch
+        g = torch.Generator(device=self.device)
+        g.manual_seed(seed * 1_000_003 + chunk)
+        z = torch.randn((rows, self.a.rank_latent), generator=g, device=self.device)
+        e = torch.randn((rows, self.a.dim), generator=g, device=self.device)
+        return z @ self.w + 0.1 * e
+
+    def quantise(self, x):
+        """f32 rows -> the tensor whose bytes are the vectors in the index's scalar kind."""
+        torch, kind = self.torch, self.a.dtype
+        if kind == "f32":
+            return x.contiguous()
+        if kind == "f16":
+            return x.half().contiguous()
+        if kind == "bf16":
+            return x.bfloat16().contiguous()
+        if kind == "i8":
+            xd = x.double()
+            return torch.clamp(torch.trunc(xd * 127.0 / xd.norm(dim=1, keepdim=True)), -127, 127).to(torch.int8).contiguous()
+        if kind == "b1":
+            bits = (x > 0).reshape(x.shape[0], -1, 8).to(torch.int32)
+            weights = torch.tensor([128, 64, 32, 16, 8, 4, 2, 1], device=x.device, dtype=torch.int32)
+            return (bits * weights).sum(dim=2).to(torch.uint8).contiguous()
+        raise ValueError(kind)
+
+    def as_float(self, q):
+        """What the metric sees, as f32 (for ground truth): b1 -> +-1 per bit."""
+        torch, kind = self.torch, self.a.dtype
+        if kind == "b1":
+            shifts = torch.tensor([7, 6, 5, 4, 3, 2, 1, 0], device=q.device, dtype=torch.int32)
+            bits = ((q.to(torch.int32)[:, :, None] >> shifts) & 1).reshape(q.shape[0], -1)
+            return bits.float() * 2 - 1
+        return q.float()
+
+    def base_chunks(self, shard: int = 0, shards: int = 1):
+        """Yields (global row ids int64, quantised rows) of this shard (keys congruent to `shard` mod `shards`)."""
+        torch = self.torch
+        for c, lo in enumerate(range(0, self.a.n, CHUNK)):
+            rows = min(CHUNK, self.a.n - lo)
+            x = self.quantise(self.rows_f32(42, c, rows))
+            ids = torch.arange(lo, lo + rows, device=self.device, dtype=torch.int64)
+            if shards > 1:
+                first = (shard - lo) % shards
+                x, ids = x[first::shards].contiguous(), ids[first::shards].contiguous()
+            yield ids, x
+
+    def queries(self, total: int, stream: int = 0):
+        out = []
+        for c, lo in enumerate(range(0, total, CHUNK)):
+            out.append(self.quantise(self.rows_f32(43 + 1000 * stream, c, min(CHUNK, total - lo))))
+        return self.torch.cat(out, 0)
 
 
-def make_base(a, shard: int, shards: int) -> tuple[np.ndarray, np.ndarray]:
-    """Rows of this shard (keys = global row ids congruent to `shard` mod `shards`)."""
-    full = datagen.latent(a.n, a.dim, seed=42, rank=a.rank_latent)
-    keys = np.arange(shard, a.n, shards, dtype=np.uint64)
-    return keys, datagen.to_scalar(full[shard::shards], a.dtype)
-
-
-def make_queries(a, total: int, stream: int = 0) -> np.ndarray:
-    return datagen.to_scalar(datagen.latent(total, a.dim, seed=43 + 1000 * stream, rank=a.rank_latent), a.dtype)
-
-
-def get_index_blob(a, shard: int, shards: int, threads: int):
-    """Build the shard's graph with the UNMODIFIED reference (production flags), or load it from cache."""
-    from oracle import bindings
-    os.makedirs(CACHE, exist_ok=True)
-    path = os.path.join(CACHE, f"index_{shard_key(a, shard, shards)}.usearch")
-    info = {"cached": os.path.exists(path)}
-    t0 = time.time()
-    keys, base = make_base(a, shard, shards)
-    info["datagen_s"] = round(time.time() - t0, 1)
-    if not os.path.exists(path):
-        ref = bindings.RefIndex("perf", metric=a.metric, scalar=a.dtype, dims=a.dim, connectivity=a.connectivity,
-                                expansion_add=a.expansion_add, expansion_search=a.ef)
-        t0 = time.time()
-        ref.add(keys, base, threads=threads)
-        info["build_s"] = round(time.time() - t0, 1)
-        info["build_threads"] = threads
-        log(f"built {len(keys)} x {a.dim} index with the reference in {info['build_s']} s on {threads} threads")
-        ref.save_path(path + ".tmp")
-        os.replace(path + ".tmp", path)
-        del ref
-    blob = np.memmap(path, dtype=np.uint8, mode="r")
-    return keys, base, blob, path, info
-
-
-def exact_topk_gpu(base: np.ndarray, keys: np.ndarray, queries: np.ndarray, metric: str, k: int, device) -> tuple:
-    """Brute-force ground truth on the GPU with torch (setup only, never timed)."""
+def build_index_gpu(a, coll: Collection, shard: int, shards: int):
+    """Generate this shard's rows on the device and link them into the graph with the batched GPU builder."""
     import torch
-    x = torch.from_numpy(np.ascontiguousarray(base)).to(device).float()
-    q = torch.from_numpy(np.ascontiguousarray(queries)).to(device).float()
-    if metric == "cos":
-        x = torch.nn.functional.normalize(x, dim=1)
+    from usearch_b200.index import Index
+    index = Index(ndim=a.dim, metric=a.metric, dtype=a.dtype, connectivity=a.connectivity, expansion_add=a.expansion_add,
+                  expansion_search=a.ef)
+    index.reserve((a.n + shards - 1) // shards)
+    t0 = time.time()
+    for ids, x in coll.base_chunks(shard, shards):
+        index.add_device(ids.data_ptr(), x.data_ptr(), x.shape[0], x.stride(0) * x.element_size(), a.dtype)
+    torch.cuda.synchronize()
+    return index, time.time() - t0
+
+
+def build_index_reference(a, coll: Collection, shard: int, shards: int, threads: int):
+    """The same rows built by the UNMODIFIED reference on the host cores (small collections / cross-checks)."""
+    import torch
+    from oracle import bindings
+    from usearch_b200.index import Index
+    keys, rows = [], []
+    for ids, x in coll.base_chunks(shard, shards):
+        keys.append(ids.cpu().numpy().astype(np.uint64))
+        rows.append(x.view(torch.uint8).reshape(x.shape[0], -1).cpu().numpy() if a.dtype == "bf16" else x.cpu().numpy())
+    base = np.concatenate(rows, 0)
+    if a.dtype == "bf16":
+        base = base.view(np.uint16)
+    ref = bindings.RefIndex("perf", metric=a.metric, scalar=a.dtype, dims=a.dim, connectivity=a.connectivity,
+                            expansion_add=a.expansion_add, expansion_search=a.ef)
+    t0 = time.time()
+    ref.add(np.concatenate(keys), base, threads=threads)
+    dt = time.time() - t0
+    blob = ref.save()
+    index = Index.restore(blob)
+    index.expansion_search = a.ef
+    return index, dt, blob
+
+
+def exact_topk_gpu(a, coll: Collection, queries_q, k: int):
+    """Brute-force ground truth over the WHOLE collection with torch (setup only, never timed)."""
+    import torch
+    q = coll.as_float(queries_q)
+    if a.metric == "cos":
         q = torch.nn.functional.normalize(q, dim=1)
-    best_d, best_i = None, None
     torch.backends.cuda.matmul.allow_tf32 = False
-    for lo in range(0, x.shape[0], 262144):
-        xs = x[lo:lo + 262144]
-        if metric in ("cos", "ip"):
-            dist = 1.0 - q @ xs.T
+    best_d = best_i = None
+    for ids, xq in coll.base_chunks():
+        x = coll.as_float(xq)
+        if a.metric == "cos":
+            x = torch.nn.functional.normalize(x, dim=1)
+        if a.metric in ("cos", "ip"):
+            dist = 1.0 - q @ x.T
+        elif a.metric == "hamming":
+            dist = (x.shape[1] - q @ x.T) * 0.5
         else:
-            dist = (q * q).sum(1, keepdim=True) - 2.0 * (q @ xs.T) + (xs * xs).sum(1)[None, :]
-        d, i = torch.topk(dist, min(k, xs.shape[0]), dim=1, largest=False)
-        i = i + lo
+            dist = (q * q).sum(1, keepdim=True) - 2.0 * (q @ x.T) + (x * x).sum(1)[None, :]
+        d, i = torch.topk(dist, min(k, x.shape[0]), dim=1, largest=False)
+        i = ids[i]
         if best_d is None:
             best_d, best_i = d, i
         else:
             cat_d, cat_i = torch.cat([best_d, d], 1), torch.cat([best_i, i], 1)
             best_d, sel = torch.topk(cat_d, k, dim=1, largest=False)
             best_i = torch.gather(cat_i, 1, sel)
-    gt_keys = torch.from_numpy(keys.astype(np.int64)).to(device)[best_i]
-    return gt_keys, best_d
+    return best_i, best_d
 
 
 def recall_at_k(found_keys: np.ndarray, counts: np.ndarray, truth: np.ndarray) -> float:
@@ -156,6 +240,14 @@ def recall_at_k(found_keys: np.ndarray, counts: np.ndarray, truth: np.ndarray) -
     for i in range(found_keys.shape[0]):
         hits += len(set(found_keys[i, :int(counts[i])].tolist()) & set(truth[i].tolist()))
     return hits / float(truth.size)
+
+
+def to_numpy_queries(a, q):
+    """Device query tensor -> the host array the C ABI / the reference take (bf16 travels as uint16)."""
+    import torch
+    if a.dtype == "bf16":
+        return q.view(torch.uint16).cpu().numpy() if hasattr(torch, "uint16") else q.view(torch.int16).cpu().numpy().view(np.uint16)
+    return q.cpu().numpy()
 
 
 # ------------------------------------------------------------------------------------------------
@@ -216,18 +308,36 @@ def cpu_reference_qps(ref, queries: np.ndarray, k: int, threads: int):
 
 
 def run_reference_arm(a):
-    """The reference's own CPU implementation of the path, all usable host threads, same graph/config."""
+    """The reference's own CPU implementation of the path, all usable host threads, on the SAME graph as our arm
+    (built on the GPU unless --builder reference, saved in the v2 format, `view`ed by the reference: no copy)."""
+    import torch
     from oracle import bindings
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl reference: the collection is generated and its graph built on a GPU")
     threads = host_threads()
-    keys, base, blob, path, info = get_index_blob(a, 0, 1, threads)
+    device = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    os.environ["USEARCH_B200_DEVICE"] = "0"
+    coll = Collection(a, device)
+    info = {"builder": a.builder}
+    if a.builder == "gpu":
+        index, dt = build_index_gpu(a, coll, 0, 1)
+        info["build_s"] = round(dt, 1)
+        t0 = time.time()
+        blob = index.save()
+        info["save_s"] = round(time.time() - t0, 1)
+    else:
+        index, dt, blob = build_index_reference(a, coll, 0, 1, threads)
+        info.update(build_s=round(dt, 1), build_threads=threads)
     ref = bindings.RefIndex("perf")
-    ref.load_path(path)
+    ref.view(blob)
     ref.change_expansion_search(a.ef)
     total = (a.warmup + a.steps) * a.batch
-    queries = make_queries(a, total)
+    q_dev = coll.queries(total)
+    queries = to_numpy_queries(a, q_dev)
     for s in range(a.warmup):
         cpu_reference_qps(ref, queries[s * a.batch:(s + 1) * a.batch], a.k, threads)
     t0 = time.perf_counter()
@@ -239,18 +349,17 @@ def run_reference_arm(a):
     qps = a.steps * a.batch / dt
     recall = None
     try:
-        import torch
-        if torch.cuda.is_available():
-            q0 = queries[a.warmup * a.batch:(a.warmup + 1) * a.batch]
-            gt, _ = exact_topk_gpu(base, keys, q0, a.metric, a.k, torch.device("cuda:0"))
-            recall = recall_at_k(found[0][0], found[0][2], gt.cpu().numpy().astype(np.uint64))
+        R = min(a.batch, 2048)
+        gt, _ = exact_topk_gpu(a, coll, q_dev[a.warmup * a.batch:a.warmup * a.batch + R], a.k)
+        recall = round(recall_at_k(found[0][0][:R], found[0][2][:R], gt.cpu().numpy().astype(np.uint64)), 4)
     except Exception as e:  # ground truth is optional for this arm
         log("ground truth skipped:", e)
     line = {
         "impl": "reference", "metric": METRIC, "value": round(qps, 1), "unit": "queries/s", "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(1000 * dt / a.steps, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
-        "config": {"workload": workload_name(a), "isa": ref.isa_name, "index_build": info},
+        "config": {"workload": workload_name(a), "isa": ref.isa_name, "index_build": info,
+                   "computed_distances_per_query": round(float(np.mean([r[3].mean() for r in found])), 1)},
         "recall_at_10": recall,
         "cpu_baseline": {"value": round(qps, 1), "unit": "queries/s", "cores": threads, "kind": "reference",
                          "sample": f"{a.steps} batches of {a.batch} queries, reference built -O3 -ffast-math -march=native, SimSIMD {ref.isa_name}"},
@@ -265,15 +374,16 @@ def run_reference_arm(a):
 
 def measure_next_rows(a, index, ref, batch: np.ndarray, k: int, threads: int) -> dict:
     """SURVEY §8(f) rows on the bench collection, outside the timed region of the headline metric: wall clock of one
-    call through the host API for the whole batch, the reference timed on a bounded sample of the same batch, and
-    label agreement on that sample. Never raises: a failure is reported in the JSON instead of losing the line."""
+    call through the host API, the reference timed on a bounded sample of the same batch, and label agreement on that
+    sample. Never raises: a failure is reported in the JSON instead of losing the line."""
     out = {}
+    batch = batch[:4096]
     try:
         index.search(batch[:256], k, exact=True)  # warm-up (scratch allocation)
         t0 = time.perf_counter()
         exact = index.search(batch, k, exact=True)
         dt = time.perf_counter() - t0
-        sample = batch[:max(4 * threads, 64)]
+        sample = batch[:max(2 * threads, 32)]
         t0 = time.perf_counter()
         want = ref.search(sample, k, threads=threads, exact=True)
         dt_cpu = time.perf_counter() - t0
@@ -306,16 +416,16 @@ def measure_next_rows(a, index, ref, batch: np.ndarray, k: int, threads: int) ->
     except Exception as e:  # noqa: BLE001
         out["cluster"] = {"error": str(e)}
     try:
-        allowed = np.arange(0, index.size, 10, dtype=np.uint64)  # one key in ten passes the predicate
+        allowed = np.arange(0, a.n, 10, dtype=np.uint64)  # one key in ten passes the predicate
         index.filtered_search(batch[:256], k, allowed)
         t0 = time.perf_counter()
         got = index.filtered_search(batch, k, allowed)
         dt = time.perf_counter() - t0
-        sample = batch[:512].astype(np.float32) if batch.dtype != np.float32 else batch[:512]
         row = {"value": round(len(batch) / dt, 1), "unit": "queries/s", "ms_per_batch": round(dt * 1e3, 2),
                "predicate": "key % 10 == 0 (bitmap over slots built on the device from the sorted key list)",
                "all_labels_pass_predicate": bool((got.keys[got.distances == got.distances] % 10 == 0).all())}
         if a.dtype == "f32":
+            sample = batch[:512]
             t0 = time.perf_counter()
             want = ref.filtered_search(sample, k, allowed, threads=threads)
             dt_cpu = time.perf_counter() - t0
@@ -331,7 +441,7 @@ def measure_next_rows(a, index, ref, batch: np.ndarray, k: int, threads: int) ->
 def run_b200_arm(a):
     import torch
     import torch.distributed as dist
-    from usearch_b200.index import Index
+    from usearch_b200 import sharded
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -344,66 +454,63 @@ def run_b200_arm(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
 
-    # shard: rank r holds the keys congruent to r mod world; replica: every rank holds everything (rank 0 builds it)
-    shards = world if a.parallelism == "shard" else 1
+    # replica: every rank holds the whole index and serves its own batches; shard: rank r holds the keys congruent to r
+    shards = world if (a.parallelism == "shard" and world > 1) else 1
     shard_id = rank if shards > 1 else 0
-    threads = max(1, host_threads() // shards)
-    if shards == 1 and world > 1:
-        if rank == 0:
-            get_index_blob(a, 0, 1, threads)
-        dist.barrier()
-    keys, base, blob, path, info = get_index_blob(a, shard_id, shards, threads)
-    t0 = time.time()
-    index = Index.restore(path)
+    threads = max(1, host_threads() // world)
+    coll = Collection(a, device)
+    info = {"builder": a.builder}
+    blob = None
+    if a.builder == "gpu":
+        index, dt = build_index_gpu(a, coll, shard_id, shards)
+        info["build_s"] = round(dt, 1)
+    else:
+        index, dt, blob = build_index_reference(a, coll, shard_id, shards, threads)
+        info.update(build_s=round(dt, 1), build_threads=threads)
     index.expansion_search = a.ef
-    info["freeze_s"] = round(time.time() - t0, 1)
-    log(f"rank {rank}: froze {index.size} vectors into HBM ({index.memory_usage / 1e9:.2f} GB) in {info['freeze_s']} s")
+    log(f"rank {rank}: {len(index)} vectors in HBM ({index.memory_usage / 1e9:.2f} GB), graph built by '{a.builder}' in {info['build_s']} s")
+    if shards > 1:
+        sharded.join(index)
 
     B, k, W, K = a.batch, a.k, a.warmup, a.steps
     total = (W + K) * B
-    queries = make_queries(a, total, stream=0 if shards > 1 or world == 1 else rank)  # replicas serve different batches
-    bpv = queries.strides[0]
+    # shards: the batch is replicated; replicas serve different batches
+    q_dev = coll.queries(total, stream=0 if (shards > 1 or world == 1) else rank)
+    bpv = q_dev.stride(0) * q_dev.element_size()
     vs = (bpv + 15) // 16 * 16
+    if vs != bpv:
+        padded = torch.zeros((total, vs), dtype=torch.uint8, device=device)
+        padded[:, :bpv] = q_dev.view(torch.uint8).reshape(total, bpv)
+        q_bytes = padded
+    else:
+        q_bytes = q_dev.view(torch.uint8).reshape(total, bpv)
 
-    # ---- device-resident inputs/outputs for the `value` measurement ----
-    q_dev = torch.zeros((total, vs), dtype=torch.uint8, device=device)
-    q_dev[:, :bpv] = torch.from_numpy(queries.view(np.uint8).reshape(total, bpv)).to(device)
     keys_dev = torch.zeros((B, k), dtype=torch.int64, device=device)
     dist_dev = torch.zeros((B, k), dtype=torch.float32, device=device)
     cnt_dev = torch.zeros(B, dtype=torch.int32, device=device)
     comp_dev = torch.zeros(B, dtype=torch.int32, device=device)
     vis_dev = torch.zeros(B, dtype=torch.int32, device=device)
     stream = torch.cuda.current_stream(device)
-
-    from usearch_b200 import sharded
-
-    def merge_topk():
-        """The single exchange step of the sharded path (usearch_b200/sharded.py): one NCCL all-gather of the
-        per-shard top-k, then a stable k-way merge ordered by (distance, shard, rank-in-shard)."""
-        mk, md, _ = sharded.merge_topk(keys_dev, dist_dev, cnt_dev, k)
-        return mk, md
+    search_device = index.sharded_search_device if shards > 1 else index.search_device
 
     def step_device(s: int):
-        qs = q_dev[s * B:(s + 1) * B]
-        index.search_device(qs.data_ptr(), B, vs, k, keys_dev.data_ptr(), dist_dev.data_ptr(), cnt_dev.data_ptr(),
-                            comp_dev.data_ptr(), vis_dev.data_ptr(), stream.cuda_stream)
-        if shards > 1:
-            return merge_topk()
-        return keys_dev, dist_dev
+        qs = q_bytes[s * B:(s + 1) * B]
+        search_device(qs.data_ptr(), B, vs, k, keys_dev.data_ptr(), dist_dev.data_ptr(), cnt_dev.data_ptr(),
+                      comp_dev.data_ptr(), vis_dev.data_ptr(), stream.cuda_stream)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(device)
 
-    # ---- warm-up (also loads every torch kernel the timed loop touches) ----
+    # ---- warm-up ----
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.5)  # nvidia-smi needs a moment before its first sample
     for s in range(W):
-        out_k, out_d = step_device(s)
-        comp_dev.sum(dtype=torch.int64), vis_dev.sum(dtype=torch.int64), out_k.clone(), cnt_dev.clone()
+        step_device(s)
+        comp_dev.sum(dtype=torch.int64), vis_dev.sum(dtype=torch.int64), keys_dev.clone(), cnt_dev.clone()
     barrier()
 
     # ---- timed: device-resident ----
@@ -415,13 +522,11 @@ def run_b200_arm(a):
     ev0.record(stream)
     first_found = None
     for s in range(W, W + K):
-        out_k, out_d = step_device(s)
+        step_device(s)
         kernel_ms.append(index.last_kernel_ms)
-        D = comp_dev.sum(dtype=torch.int64)
-        H = vis_dev.sum(dtype=torch.int64)
-        alg_bytes.append((D, H))
+        alg_bytes.append((comp_dev.sum(dtype=torch.int64), vis_dev.sum(dtype=torch.int64)))
         if first_found is None:
-            first_found = (out_k.clone(), cnt_dev.clone())
+            first_found = (keys_dev.clone(), dist_dev.clone(), cnt_dev.clone())
             first_counters = (comp_dev.cpu().numpy().astype(np.uint64), vis_dev.cpu().numpy().astype(np.uint64))
     ev1.record(stream)
     barrier()
@@ -437,20 +542,16 @@ def run_b200_arm(a):
     h_per_q = sum(int(H.item()) for _, H in alg_bytes) / (K * B)
 
     # ---- timed: end to end through the host C ABI (pinned host buffers, H2D + D2H inside) ----
-    q_pin = torch.from_numpy(queries.view(np.uint8).reshape(total, bpv)).pin_memory()
-    q_host = q_pin.numpy().view(queries.dtype).reshape(queries.shape)
+    q_pin = q_dev.view(torch.uint8).reshape(total, bpv).cpu().pin_memory()
+    np_dtype = {"f32": np.float32, "f16": np.float16, "bf16": np.uint16, "i8": np.int8, "b1": np.uint8}[a.dtype]
+    q_host = q_pin.numpy().view(np_dtype).reshape(total, -1)
+    search_host = index.sharded_search if shards > 1 else index.search
     for s in range(W):
-        index.search(q_host[s * B:(s + 1) * B], k)
+        search_host(q_host[s * B:(s + 1) * B], k)
     barrier()
     t0 = time.perf_counter()
     for s in range(W, W + K):
-        res = index.search(q_host[s * B:(s + 1) * B], k)
-        if shards > 1:
-            keys_dev.copy_(torch.from_numpy(res.keys.view(np.int64)), non_blocking=False)
-            dist_dev.copy_(torch.from_numpy(res.distances), non_blocking=False)
-            cnt_dev.copy_(torch.from_numpy(res.counts.astype(np.int32)), non_blocking=False)
-            mk, md = merge_topk()
-            mk.cpu()
+        res = search_host(q_host[s * B:(s + 1) * B], k)
     barrier()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], device=device)
@@ -458,35 +559,37 @@ def run_b200_arm(a):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te.item())
 
-    # ---- quality gate: recall@10 against exact ground truth over the whole (sharded) collection ----
-    R = min(B, 8192)  # rows of the first timed batch that are checked: a [rows x 262144] distance block must fit in HBM
-    q0 = queries[W * B:W * B + R]
-    gt_k, gt_d = exact_topk_gpu(base, keys, q0, a.metric, k, device)
-    if shards > 1:
-        gk = [torch.zeros_like(gt_k) for _ in range(world)]
-        gd = [torch.zeros_like(gt_d) for _ in range(world)]
-        dist.all_gather(gk, gt_k)
-        dist.all_gather(gd, gt_d)
-        sel = torch.topk(torch.cat(gd, 1), k, dim=1, largest=False).indices
-        gt_k = torch.gather(torch.cat(gk, 1), 1, sel)
-    found_k, found_c = first_found
-    counts = (found_c.cpu().numpy() if shards == 1 else np.full(B, k))[:R]
-    recall = recall_at_k(found_k.cpu().numpy().astype(np.uint64)[:R], counts, gt_k.cpu().numpy().astype(np.uint64))
+    # ---- quality gate: recall@10 against exact ground truth over the whole collection ----
+    R = min(B, 2048)
+    q0 = q_dev[W * B:W * B + R]
+    gt_k, gt_d = exact_topk_gpu(a, coll, q0, k)
+    found_k, found_d, found_c = first_found
+    recall = recall_at_k(found_k.cpu().numpy().astype(np.uint64)[:R], found_c.cpu().numpy()[:R], gt_k.cpu().numpy().astype(np.uint64))
+    if world > 1:  # every rank checks its own batch (replicas) or the same merged batch (shards)
+        rt = torch.tensor([recall], device=device)
+        dist.all_reduce(rt, op=dist.ReduceOp.MIN)
+        recall = float(rt.item())
 
     if rank != 0:
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
         return
 
-    # ---- CPU baseline on a bounded sample (rank 0, N=1 only) ----
+    # ---- CPU baseline on a bounded sample + full-size parity (rank 0, N=1 only) ----
     cpu = None
     next_rows = None
     if world == 1 and not a.no_cpu_baseline:
         from oracle import bindings
         threads_all = host_threads()
+        t0 = time.time()
+        if blob is None:
+            blob = index.save()
+        info["save_s"] = round(time.time() - t0, 1)
         ref = bindings.RefIndex("perf")
-        ref.load_path(path)
+        ref.view(blob)
         ref.change_expansion_search(a.ef)
+        queries = q_host
         pilot_qps, _, _ = cpu_reference_qps(ref, queries[:256], k, threads_all)
         sample = int(min(total, max(512, pilot_qps * a.cpu_sample_seconds)))
         qps_cpu, dt_cpu, res_cpu = cpu_reference_qps(ref, queries[:sample], k, threads_all)
@@ -494,16 +597,33 @@ def run_b200_arm(a):
                "sample": f"{sample} queries of the same workload in {dt_cpu:.1f} s, reference -O3 -ffast-math -march=native, SimSIMD {ref.isa_name}",
                "computed_distances_per_query": round(float(res_cpu[3].mean()), 1),
                "visited_members_per_query": round(float(res_cpu[4].mean()), 1)}
-        # full-size parity property: the first timed batch, GPU vs the reference's NATIVE SimSIMD kernels on the
-        # same graph (cosine differs by <= 1 ULP from the pinned arithmetic, so near-ties may swap)
-        lo, hi = W * B, (W + 1) * B
-        if sample >= hi:
-            gpu_keys = found_k.cpu().numpy().astype(np.uint64)
-            same_rows = (res_cpu[0][lo:hi] == gpu_keys).all(axis=1)
-            cpu["gpu_rows_with_identical_labels"] = round(float(same_rows.mean()), 6)
-            cpu["gpu_counters_identical"] = bool(np.array_equal(res_cpu[3][lo:hi], first_counters[0]) and
-                                                 np.array_equal(res_cpu[4][lo:hi], first_counters[1]))
-        next_rows = measure_next_rows(a, index, ref, queries[W * B:(W + 1) * B], k, threads_all)
+        # full-size parity property on the first timed batch (<= 4096 rows): labels + counters against the reference's
+        # NATIVE SimSIMD kernels (cosine differs by <= 1 ULP from the pinned arithmetic, so near-ties may swap), and
+        # labels + distance BITS + counters against the reference with the metric pinned (oracle/metrics_pinned.h)
+        P = min(B, 4096)
+        lo = W * B
+        gpu_keys = found_k.cpu().numpy().astype(np.uint64)[:P]
+        gpu_bits = found_d.cpu().numpy().view(np.uint32)[:P]
+        native = ref.search(queries[lo:lo + P], k, threads=threads_all, counters=True)
+        cpu["gpu_rows_with_identical_labels"] = round(float((native[0] == gpu_keys).all(axis=1).mean()), 6)
+        cpu["gpu_counters_identical"] = bool(np.array_equal(native[3], first_counters[0][:P]) and
+                                             np.array_equal(native[4], first_counters[1][:P]))
+        try:
+            pinned_ref = bindings.RefIndex("parity")
+            pinned_ref.view(blob)
+            pinned_ref.change_expansion_search(a.ef)
+            pinned_ref.pin_metric(True)
+            pinned = pinned_ref.search(queries[lo:lo + P], k, threads=threads_all, counters=True)
+            cpu["parity_rows_checked"] = P
+            cpu["parity_pinned_rows_with_identical_labels"] = round(float((pinned[0] == gpu_keys).all(axis=1).mean()), 6)
+            cpu["parity_pinned_distance_bits_identical"] = bool(np.array_equal(pinned[1].view(np.uint32), gpu_bits))
+            cpu["parity_pinned_counters_identical"] = bool(np.array_equal(pinned[3], first_counters[0][:P]) and
+                                                           np.array_equal(pinned[4], first_counters[1][:P]))
+            del pinned_ref
+        except Exception as e:  # noqa: BLE001
+            cpu["parity_pinned_error"] = str(e)
+        if not a.no_next_rows:
+            next_rows = measure_next_rows(a, index, ref, queries[lo:lo + B], k, threads_all)
         del ref
 
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -513,47 +633,52 @@ def run_b200_arm(a):
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     k_ms = float(np.mean(kernel_ms))
     achieved = float(np.mean(alg)) / (k_ms * 1e-3) / 1e9
-    traffic = None
+    traffic = None  # DRAM bytes per launch from an `ncu --set full` capture of this very workload at this N, else null
     prof = os.path.join(ROOT, "profiles", "roofline_latest.json")
     if os.path.exists(prof):
         try:
             pj = json.load(open(prof))
-            if pj.get("workload") == workload_name(a):
+            if pj.get("workload") == workload_name(a) and int(pj.get("n_gpus", 1)) == world and pj.get("parallelism", "replica") == a.parallelism:
                 traffic = pj.get("dram_bytes_per_launch")
         except Exception:
             pass
 
-    units = world * B * K  # every rank searched every query of every step against its shard
-    value = units / (elapsed_ms * 1e-3)
+    # the metric is job throughput: queries answered per second. Replicas answer `world` different batches per step,
+    # shards answer ONE batch per step between them.
+    queries_per_step = B * (world if shards == 1 else 1)
+    value = queries_per_step * K / (elapsed_ms * 1e-3)
+    parallelism = "single GPU" if world == 1 else (
+        f"shard-by-key x{world}: every rank searches the whole batch in its shard, one NCCL all-gather + merge kernel" if shards > 1
+        else f"{world} replicas of the whole index, one batch of {B} per replica per step, no exchange step")
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": "queries/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": round(elapsed_ms / K, 3), "higher_is_better": True, "scaling": "weak" if shards == 1 else "strong",
         "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
         "config": {
-            "workload": workload_name(a), "parallelism": "single GPU" if world == 1 else (f"shard-by-key x{world} + NCCL all-gather top-k" if shards > 1 else
-                                                                         f"{world} replicas of the whole index, one batch each, no exchange"),
+            "workload": workload_name(a), "parallelism": parallelism, "queries_per_step": queries_per_step,
             "l2_policy": "index (vectors+graph) larger than the 126 MB L2; every step uses a fresh query batch",
             "index_hbm_gb": round(index.memory_usage / 1e9, 3), "index_build": info,
             "computed_distances_per_query": round(d_per_q, 1), "visited_members_per_query": round(h_per_q, 1),
-            "job_qps": round(B * K / (elapsed_ms * 1e-3), 1),
         },
         "recall_at_10": round(recall, 4),
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "e2e": {"value": round(world * B * K / e2e_s, 1), "unit": "queries/s", "h2d_bytes_per_step": int(B * bpv),
-                "d2h_bytes_per_step": int(B * k * 12 + B * 4 + B * 4),
-                "note": "usearch_search_many on pinned host buffers; H2D of queries and D2H of keys/distances/counts inside the timed call"},
+        "e2e": {"value": round(queries_per_step * K / e2e_s, 1), "unit": "queries/s", "h2d_bytes_per_step": int(B * bpv),
+                "d2h_bytes_per_step": int(B * k * 12 + B * 4),
+                "note": ("usearch_b200_sharded_search_many" if shards > 1 else "usearch_search_many") +
+                        " on pinned host buffers; H2D of queries and D2H of keys/distances/counts inside the timed call"},
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                      "kernel": "hnsw_search_kernel", "kernel_ms_per_launch": round(k_ms, 3),
                      "algorithmic_bytes_per_launch": int(np.mean(alg)),
-                     "formula": "sum_q D_q*bytes_per_vector + H_q*(4+4*M0), D/H = the reference's computed_distances/visited_members"},
+                     "formula": "sum_q D_q*bytes_per_vector + H_q*(4+4*M0), D/H = the reference's computed_distances/visited_members; rank 0's launch"},
         "cpu_baseline": cpu,
     }
     if next_rows:
         line["next_rows"] = next_rows
     print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

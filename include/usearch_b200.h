@@ -167,6 +167,30 @@ void usearch_b200_add_many(usearch_index_t index, usearch_key_t const* keys, voi
 void usearch_b200_add_many_device(usearch_index_t index, usearch_key_t const* keys, void const* vectors, size_t count,
                                   size_t vectors_stride, usearch_scalar_kind_t vector_kind, usearch_error_t* error);
 
+/* ---- additive: sharded search, one process per GPU ------------------------------------------------ */
+
+/* The reference's `Indexes` (python/lib.cpp:74-107, :321-402) searches every query in every shard and merges by distance. Here
+ * each process holds one shard on its GPU. Rank 0 obtains a 128-byte id (an ncclUniqueId), the host side hands it to every
+ * rank over its own control plane (torch.distributed, MPI, a file), every rank joins. A sharded search = this shard's batched
+ * search + ONE NCCL all-gather of the packed per-shard rows + a k-way merge kernel ordered by (distance, shard, position);
+ * every rank receives the merged rows. Collective: all ranks must call with the same queries and count. */
+void usearch_b200_shards_unique_id(void* unique_id128, usearch_error_t* error);
+void usearch_b200_shards_join(usearch_index_t index, int rank, int world, void const* unique_id128, usearch_error_t* error);
+size_t usearch_b200_sharded_search_many(usearch_index_t index, void const* queries, size_t queries_count, size_t queries_stride,
+                                        usearch_scalar_kind_t query_kind, size_t count, usearch_key_t* keys,
+                                        usearch_distance_t* distances, size_t* counts, usearch_error_t* error);
+/* device pointers, queries already in the index's scalar kind (see usearch_b200_search_many_device) */
+void usearch_b200_sharded_search_many_device(usearch_index_t index, void const* queries, size_t queries_count,
+                                             size_t queries_stride, size_t count, usearch_key_t* keys,
+                                             usearch_distance_t* distances, uint32_t* counts, uint32_t* computed_distances,
+                                             uint32_t* visited_members, void* cuda_stream, usearch_error_t* error);
+/* The merge on its own (search_result_t::merge_into, index.hpp:2650-2670, made deterministic), for callers that hold several
+ * shards in one process: `payloads` = `world` blocks of usearch_b200_shards_payload_bytes(queries_count, count) bytes in HOST
+ * memory, each `keys u64[nq*count] | distances f32[nq*count] | counts u32[nq]` (16-byte padded). */
+size_t usearch_b200_shards_payload_bytes(size_t queries_count, size_t count);
+void usearch_b200_merge_topk(void const* payloads, int world, size_t queries_count, size_t count, usearch_key_t* keys,
+                             usearch_distance_t* distances, uint32_t* counts, usearch_error_t* error);
+
 /* ---- additive, device-resident variants ---------------------------------------------------- */
 
 /* All pointers are DEVICE pointers on the index's GPU; `queries` must already be in the index's

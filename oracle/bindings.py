@@ -74,6 +74,7 @@ def ref_lib(flavour: str = "parity") -> C.CDLL | None:
     lib.ref_remove.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_char_p)]
     lib.ref_save_buffer.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_char_p)]
     lib.ref_load_buffer.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_char_p)]
+    lib.ref_view_buffer.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_char_p)]
     lib.ref_save_path.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_char_p)]
     lib.ref_load_path.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_char_p)]
     lib.ref_search_many.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int,
@@ -163,6 +164,14 @@ class RefIndex:
         err = C.c_char_p()
         self.lib.ref_load_buffer(self.h, _ptr(blob), blob.size, C.byref(err))
         _check(err)
+
+    def view(self, blob: np.ndarray) -> None:
+        """`view` over the caller's buffer: nothing is copied, the buffer is kept alive by this object."""
+        blob = np.ascontiguousarray(blob, dtype=np.uint8)
+        err = C.c_char_p()
+        self.lib.ref_view_buffer(self.h, _ptr(blob), blob.size, C.byref(err))
+        _check(err)
+        self._keep = blob
 
     def save_path(self, path: str) -> None:
         err = C.c_char_p()

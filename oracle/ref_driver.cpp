@@ -325,6 +325,19 @@ void ref_load_buffer(void* h, void const* buffer, std::size_t length, char const
     r->threads = 0;
 }
 
+/* index_dense_gt::view over caller memory (index_dense.hpp:1190-1313): no copy of the vectors; the caller keeps `buffer` alive */
+void ref_view_buffer(void* h, void const* buffer, std::size_t length, char const** error) {
+    *error = nullptr;
+    auto* r = static_cast<ref_index_t*>(h);
+    memory_mapped_file_t map(static_cast<byte_t*>(const_cast<void*>(buffer)), length);
+    auto result = r->index.view(std::move(map));
+    if (!result) {
+        *error = result.error.release();
+        return;
+    }
+    r->threads = 0;
+}
+
 void ref_save_path(void* h, char const* path, char const** error) {
     *error = nullptr;
     auto result = static_cast<ref_index_t*>(h)->index.save(path);

@@ -89,6 +89,7 @@ def case(name, n, d, metric, scalar, m, nq=1000, efs=(16, 64, 128), threads=8):
     t_gpu = time.time() - t0
     gpu_blob = index.save()
     rep = structure_report(gpu_blob)
+    rep["reference_mean_degree0"] = structure_report(ref_blob)["mean_degree0"]
     truth = hamming_truth(base, queries, 10) if scalar == "b1" else exact_truth(
         base if scalar != "bf16" else (base.astype(np.uint32) << 16).view(np.float32),
         queries if scalar != "bf16" else (queries.astype(np.uint32) << 16).view(np.float32), metric, 10)
@@ -133,17 +134,23 @@ def main():
     p = argparse.ArgumentParser()
     p.add_argument("--big", action="store_true")
     p.add_argument("--only-tiny", action="store_true")
+    p.add_argument("--cases", default="", help="comma-separated case names (default: all)")
     a = p.parse_args()
-    case("tiny", 300, 32, "cos", "f32", 8, nq=100)
-    if a.only_tiny:
-        return
-    case("latent32", 20000, 32, "cos", "f32", 16)
-    case("l2_128", 20000, 128, "l2sq", "f32", 16)
-    case("f16", 20000, 96, "cos", "f16", 16)
-    case("bf16", 10000, 64, "ip", "bf16", 16)
-    case("i8", 20000, 128, "ip", "i8", 16)
-    case("b1", 20000, 256, "hamming", "b1", 32)
-    case("wide", 20000, 768, "cos", "f32", 32, nq=500)
+    cases = {
+        "tiny": (300, 32, "cos", "f32", 8, 100),
+        "latent32": (20000, 32, "cos", "f32", 16, 1000),
+        "l2_128": (20000, 128, "l2sq", "f32", 16, 1000),
+        "f16": (20000, 96, "cos", "f16", 16, 1000),
+        "bf16": (10000, 64, "ip", "bf16", 16, 1000),
+        "i8": (20000, 128, "ip", "i8", 16, 1000),
+        "b1": (20000, 256, "hamming", "b1", 32, 1000),
+        "wide": (20000, 768, "cos", "f32", 32, 500),
+        "l2_100k": (100000, 128, "l2sq", "f32", 16, 1000),
+    }
+    wanted = ["tiny"] if a.only_tiny else ([c for c in a.cases.split(",") if c] or [c for c in cases if c != "l2_100k"])
+    for name in wanted:
+        n, d, metric, scalar, m, nq = cases[name]
+        case(name, n, d, metric, scalar, m, nq=nq)
     if a.big:
         n, d = 1_000_000, 768
         from usearch_b200 import datagen

@@ -462,6 +462,51 @@ size_t usearch_b200_exact_search_many(usearch_index_t index, void const* queries
     return total;
 }
 
+/* ---- sharded search: one process per GPU, one shard per process (python/lib.cpp:321-402 `Indexes`) ------------------ */
+
+void usearch_b200_shards_unique_id(void* unique_id128, usearch_error_t* error) { set_error(error, shards_unique_id(unique_id128)); }
+
+void usearch_b200_shards_join(usearch_index_t index, int rank, int world, void const* unique_id128, usearch_error_t* error) {
+    frozen_index_t* ix = as_index(index);
+    std::lock_guard<std::mutex> lock(ix->mutex);
+    set_error(error, ix->join_shards(rank, world, unique_id128));
+}
+
+size_t usearch_b200_sharded_search_many(usearch_index_t index, void const* queries, size_t queries_count, size_t queries_stride,
+                                        usearch_scalar_kind_t query_kind, size_t count, usearch_key_t* keys,
+                                        usearch_distance_t* distances, size_t* counts, usearch_error_t* error) {
+    frozen_index_t* ix = as_index(index);
+    uint32_t qs = scalar_to_char(query_kind);
+    if (!qs) { set_error(error, "Unknown scalar kind!"); return 0; }
+    if (char const* e = ix->sharded_search_host(queries, queries_count, queries_stride, qs, count, keys, distances, counts)) {
+        set_error(error, e);
+        return 0;
+    }
+    size_t total = 0;
+    if (counts)
+        for (size_t i = 0; i < queries_count; ++i) total += counts[i];
+    return total;
+}
+
+void usearch_b200_sharded_search_many_device(usearch_index_t index, void const* queries, size_t queries_count, size_t queries_stride,
+                                             size_t count, usearch_key_t* keys, usearch_distance_t* distances, uint32_t* counts,
+                                             uint32_t* computed_distances, uint32_t* visited_members, void* cuda_stream,
+                                             usearch_error_t* error) {
+    frozen_index_t* ix = as_index(index);
+    std::lock_guard<std::mutex> lock(ix->mutex);
+    if (char const* e = ix->ensure_context()) return set_error(error, e);
+    cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ix->stream;
+    set_error(error, ix->sharded_search_device(queries, queries_count, queries_stride, count, keys, distances, counts,
+                                               computed_distances, visited_members, s));
+}
+
+size_t usearch_b200_shards_payload_bytes(size_t queries_count, size_t count) { return shards_payload_bytes(queries_count, count); }
+
+void usearch_b200_merge_topk(void const* payloads, int world, size_t queries_count, size_t count, usearch_key_t* keys,
+                             usearch_distance_t* distances, uint32_t* counts, usearch_error_t* error) {
+    set_error(error, shards_merge_host(payloads, world, queries_count, count, keys, distances, counts));
+}
+
 void usearch_clear(usearch_index_t index, usearch_error_t*) {
     frozen_index_t* ix = as_index(index);
     std::lock_guard<std::mutex> lock(ix->mutex);

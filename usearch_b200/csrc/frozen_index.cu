@@ -61,6 +61,7 @@ size_t bits_per_scalar(uint32_t s) { /* index_plugins.hpp:237-257 */
 }
 
 frozen_index_t::~frozen_index_t() {
+    leave_shards();
     release_device();
     if (stream) cudaStreamDestroy(stream);
     if (ev_begin) cudaEventDestroy(ev_begin);

@@ -171,6 +171,8 @@ struct build_scratch_t {
     }
 };
 
+struct shard_group_t; /* shards.cu */
+
 struct frozen_index_t {
     /* configuration (usearch_init_options_t) */
     uint32_t metric = 0, scalar = 0; /* reference char codes */
@@ -243,6 +245,15 @@ struct frozen_index_t {
     char const* rename_key(uint64_t from, uint64_t to, size_t* renamed);
     char const* get_vectors(uint64_t key, size_t max_count, void* out, uint32_t out_scalar, size_t* found);
 
+    /* sharded search (shards.cu): this handle is shard `rank` of `world`, one process per GPU */
+    shard_group_t* shards = nullptr;
+    char const* join_shards(int rank, int world, void const* unique_id128);
+    void leave_shards();
+    char const* sharded_search_device(void const* d_queries, size_t nq, size_t stride, size_t k, uint64_t* d_keys, float* d_dists,
+                                      uint32_t* d_counts, uint32_t* d_computed, uint32_t* d_cycles, cudaStream_t stream);
+    char const* sharded_search_host(void const* queries, size_t nq, size_t stride, uint32_t query_scalar, size_t k, uint64_t* keys,
+                                    float* dists, size_t* counts);
+
     /* searches */
     char const* plan(uint32_t k, uint32_t visited_cap_override, launch_plan_t& plan, uint32_t ef_override = 0) const;
     char const* prepare_launch(launch_plan_t const& pl, size_t warps, search_args_t& a, cudaStream_t s);
@@ -277,6 +288,11 @@ char const* exact_search_device(device_index_t const& ix, int sm_count, void con
 char const* exact_search_free(void const* dataset, size_t dataset_count, size_t dataset_stride, void const* queries,
                               size_t queries_count, size_t queries_stride, uint32_t scalar, size_t dimensions, uint32_t metric,
                               size_t count, uint64_t* keys, size_t keys_stride, float* distances, size_t distances_stride);
+
+/* shards.cu */
+char const* shards_unique_id(void* out128);
+size_t shards_payload_bytes(size_t nq, size_t k);
+char const* shards_merge_host(void const* payloads, int world, size_t nq, size_t k, uint64_t* keys, float* dists, uint32_t* counts);
 
 /* builder.cu: scalar casts and single-pair distances on the device */
 char const* cast_rows_device(uint8_t const* src, size_t src_stride, uint32_t from, uint8_t* dst, size_t dst_stride, uint32_t to,

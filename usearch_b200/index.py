@@ -51,6 +51,8 @@ EXPORTED_SYMBOLS = [
     "usearch_b200_filtered_search_many", "usearch_b200_exact_search_many", "usearch_b200_cluster_many",
     "usearch_b200_profile_phases", "usearch_b200_device", "usearch_b200_kernel_launches", "usearch_b200_last_kernel_ms",
     "usearch_b200_bytes_per_vector", "usearch_b200_max_level", "usearch_b200_add_many", "usearch_b200_add_many_device",
+    "usearch_b200_shards_unique_id", "usearch_b200_shards_join", "usearch_b200_sharded_search_many",
+    "usearch_b200_sharded_search_many_device", "usearch_b200_shards_payload_bytes", "usearch_b200_merge_topk",
 ]
 
 
@@ -133,6 +135,17 @@ def load_library() -> C.CDLL:
     lib.usearch_remove.argtypes = [C.c_void_p, C.c_uint64, err]
     lib.usearch_rename.restype = C.c_size_t
     lib.usearch_rename.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, err]
+    lib.usearch_b200_shards_unique_id.argtypes = [C.c_void_p, err]
+    lib.usearch_b200_shards_join.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, err]
+    lib.usearch_b200_sharded_search_many.restype = C.c_size_t
+    lib.usearch_b200_sharded_search_many.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_size_t,
+                                                     C.c_void_p, C.c_void_p, C.c_void_p, err]
+    lib.usearch_b200_sharded_search_many_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t,
+                                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                            C.c_void_p, err]
+    lib.usearch_b200_shards_payload_bytes.restype = C.c_size_t
+    lib.usearch_b200_shards_payload_bytes.argtypes = [C.c_size_t, C.c_size_t]
+    lib.usearch_b200_merge_topk.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, err]
     lib.usearch_distance.restype = C.c_float
     lib.usearch_distance.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_int, err]
     _lib = lib
@@ -491,6 +504,40 @@ class Index:
         return {"queries": int(out[7]), **{n: float(out[i]) / q for i, n in enumerate(names)},
                 "pushes": float(out[8]) / q, "avg_max_heap": float(out[9]) / q, "max_heap": int(out[10])}
 
+    # ---- sharded search: this index is one shard of a group of processes (shards.cu) ------------------------
+    def join_shards(self, rank: int, world: int, unique_id: bytes) -> None:
+        """Collective. `unique_id` = the 128 bytes rank 0 got from :func:`shards_unique_id`, handed to every rank."""
+        err = C.c_char_p()
+        buf = (C.c_char * 128).from_buffer_copy(unique_id)
+        self._lib.usearch_b200_shards_join(self._h, rank, world, buf, C.byref(err))
+        _raise(err)
+
+    def sharded_search(self, vectors: np.ndarray, count: int = 10) -> BatchMatches:
+        """Collective: every rank passes the same queries and receives the merged top-`count` of all shards."""
+        vectors = np.ascontiguousarray(vectors)
+        if vectors.ndim == 1:
+            vectors = vectors[None, :]
+        kind = self._kind_of(vectors)
+        nq = vectors.shape[0]
+        keys = np.zeros((nq, count), dtype=np.uint64)
+        distances = np.zeros((nq, count), dtype=np.float32)
+        counts = np.zeros(nq, dtype=np.uint64)
+        err = C.c_char_p()
+        self._lib.usearch_b200_sharded_search_many(self._h, vectors.ctypes.data_as(C.c_void_p), nq, vectors.strides[0],
+                                                   SCALAR_KIND[kind], count, keys.ctypes.data_as(C.c_void_p),
+                                                   distances.ctypes.data_as(C.c_void_p), counts.ctypes.data_as(C.c_void_p),
+                                                   C.byref(err))
+        _raise(err)
+        return BatchMatches(keys, distances, counts)
+
+    def sharded_search_device(self, queries_ptr: int, nq: int, stride: int, count: int, keys_ptr: int, distances_ptr: int,
+                              counts_ptr: int, computed_ptr: int = 0, visited_ptr: int = 0, stream: int = 0) -> None:
+        err = C.c_char_p()
+        self._lib.usearch_b200_sharded_search_many_device(self._h, queries_ptr, nq, stride, count, keys_ptr, distances_ptr,
+                                                          counts_ptr, computed_ptr or None, visited_ptr or None,
+                                                          stream or None, C.byref(err))
+        _raise(err)
+
     def search_device(self, queries_ptr: int, nq: int, stride: int, count: int, keys_ptr: int, distances_ptr: int,
                       counts_ptr: int, computed_ptr: int = 0, visited_ptr: int = 0, stream: int = 0) -> None:
         """Device-resident batch: raw device pointers (e.g. ``tensor.data_ptr()``) and a CUDA stream handle."""
@@ -522,3 +569,36 @@ def exact_search(dataset: np.ndarray, queries: np.ndarray, count: int = 10, *, m
                              distances.ctypes.data_as(C.c_void_p), distances.strides[0], C.byref(err))
     _raise(err)
     return BatchMatches(keys, distances, np.full(nq, count, dtype=np.uint64))
+
+
+def shards_unique_id() -> bytes:
+    """The 128-byte group id (an ncclUniqueId) rank 0 creates; every rank passes it to `Index.join_shards`."""
+    lib = load_library()
+    buf = (C.c_char * 128)()
+    err = C.c_char_p()
+    lib.usearch_b200_shards_unique_id(buf, C.byref(err))
+    _raise(err)
+    return bytes(buf)
+
+
+def merge_topk(shard_results, count: int) -> BatchMatches:
+    """The merge kernel on its own: `shard_results` = per-shard (keys [nq,count] u64, distances [nq,count] f32, counts [nq]),
+    as `Indexes` would merge them (python/lib.cpp:350-391) but ordered by (distance, shard, position)."""
+    lib = load_library()
+    world = len(shard_results)
+    nq = shard_results[0][0].shape[0]
+    size = lib.usearch_b200_shards_payload_bytes(nq, count)
+    blob = np.zeros(world * size, dtype=np.uint8)
+    for r, (k, d, c) in enumerate(shard_results):
+        base = r * size
+        blob[base:base + nq * count * 8] = np.ascontiguousarray(k, dtype=np.uint64).view(np.uint8).ravel()
+        blob[base + nq * count * 8:base + nq * count * 12] = np.ascontiguousarray(d, dtype=np.float32).view(np.uint8).ravel()
+        blob[base + nq * count * 12:base + nq * count * 12 + nq * 4] = np.ascontiguousarray(c).astype(np.uint32).view(np.uint8)
+    keys = np.zeros((nq, count), dtype=np.uint64)
+    distances = np.zeros((nq, count), dtype=np.float32)
+    counts = np.zeros(nq, dtype=np.uint32)
+    err = C.c_char_p()
+    lib.usearch_b200_merge_topk(blob.ctypes.data_as(C.c_void_p), world, nq, count, keys.ctypes.data_as(C.c_void_p),
+                                distances.ctypes.data_as(C.c_void_p), counts.ctypes.data_as(C.c_void_p), C.byref(err))
+    _raise(err)
+    return BatchMatches(keys, distances, counts.astype(np.uint64))
