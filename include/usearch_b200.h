@@ -153,7 +153,7 @@ void usearch_exact_search(void const* dataset, size_t dataset_size, size_t datas
                           size_t queries_size, size_t queries_stride, usearch_scalar_kind_t scalar_kind, size_t dimensions,
                           usearch_metric_kind_t metric_kind, size_t count, size_t threads, usearch_key_t* keys,
                           size_t keys_stride, usearch_distance_t* distances, size_t distances_stride,
-                          usearch_error_t* error); /* usearch.h:467; runs on the GPU, `threads` ignored, count <= 256 */
+                          usearch_error_t* error); /* usearch.h:467; runs on the GPU, `threads` ignored; count > 256 needs vectors that fit the tiled stage (about 3.5 KB) */
 void usearch_clear(usearch_index_t index, usearch_error_t* error); /* usearch.h:481 */
 
 /* NEW (additive). GPU-assisted construction: `count` keys and vectors in one call. The vectors (any
@@ -197,12 +197,23 @@ void usearch_b200_merge_topk(void const* payloads, int world, size_t queries_cou
  * scalar kind, rows `queries_stride` bytes apart (a multiple of 16 or equal to bytes-per-vector).
  * `keys`/`distances` are dense [queries_count x count]; `counts`, `computed_distances` and
  * `visited_members` (the reference's per-query counters, index.hpp:2605-2609; may be NULL) are
- * uint32 [queries_count]. `cuda_stream` is a cudaStream_t (NULL = default stream). The call only
- * enqueues work; it synchronises nothing unless a scratch overflow forces a retry. */
+ * uint32 [queries_count]. `cuda_stream` is a cudaStream_t (NULL = the handle's own stream). Nothing is copied; the call
+ * returns when the batch is complete (it waits for the kernel to read the per-query status words and retries scratch
+ * overflows). For launches that do not wait, see usearch_b200_search_many_enqueue / _finish below. */
 void usearch_b200_search_many_device(usearch_index_t index, void const* queries, size_t queries_count,
                                      size_t queries_stride, size_t count, usearch_key_t* keys,
                                      usearch_distance_t* distances, uint32_t* counts, uint32_t* computed_distances,
                                      uint32_t* visited_members, void* cuda_stream, usearch_error_t* error);
+
+/* The asynchronous pair. `enqueue` = the same arguments as usearch_b200_search_many_device, but it ONLY enqueues the
+ * kernel on `cuda_stream` and returns; any number of batches may be in flight. `finish` waits for them, inspects the
+ * per-query status words and re-runs, with larger scratch, the rare queries whose scratch overflowed; the outputs of
+ * every enqueued batch are final when it returns. */
+void usearch_b200_search_many_enqueue(usearch_index_t index, void const* queries, size_t queries_count,
+                                      size_t queries_stride, size_t count, usearch_key_t* keys,
+                                      usearch_distance_t* distances, uint32_t* counts, uint32_t* computed_distances,
+                                      uint32_t* visited_members, void* cuda_stream, usearch_error_t* error);
+void usearch_b200_search_many_finish(usearch_index_t index, usearch_error_t* error);
 
 /* Like usearch_search_many (host buffers) but also returns the reference's two counters. */
 size_t usearch_b200_search_many_stats(usearch_index_t index, void const* queries, size_t queries_count,
@@ -232,7 +243,7 @@ void usearch_b200_cluster_many(usearch_index_t index, void const* queries, size_
 
 /* `search(exact = true)` of the reference's C++ / Python surface (index.hpp:3047-3051, search_exact_ :4251-4268) for a
  * batch: brute force over every non-removed member of the frozen index, ties resolved exactly like the reference's
- * sequence of sorted inserts (equal distances: larger slot first). count <= 256. */
+ * sequence of sorted inserts (equal distances: larger slot first). Any count; beyond 256 the lists live in L2 instead of registers. */
 size_t usearch_b200_exact_search_many(usearch_index_t index, void const* queries, size_t queries_count,
                                       size_t queries_stride, usearch_scalar_kind_t query_kind, size_t count,
                                       usearch_key_t* keys, usearch_distance_t* distances, size_t* counts,
@@ -243,6 +254,9 @@ size_t usearch_b200_exact_search_many(usearch_index_t index, void const* queries
  * cycles of setup+descent | heap pop | row + visited test | vector wait | distance math | accept replay |
  * output, then queries | heap pushes | sum of per-query max heap size | max heap size | 5 reserved. */
 void usearch_b200_profile_phases(usearch_index_t index, int enable, uint64_t* counters16);
+/* Tuning knobs of the search launch for this handle ("stage_sets", "warps_per_sm", "issue_per_lane", "prefetch"); results
+ * never depend on them. Returns 0, or -1 for an unknown knob. */
+int usearch_b200_tune(usearch_index_t index, char const* knob, int value);
 int usearch_b200_device(usearch_index_t index);
 uint64_t usearch_b200_kernel_launches(usearch_index_t index);
 float usearch_b200_last_kernel_ms(usearch_index_t index);

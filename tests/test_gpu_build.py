@@ -207,3 +207,33 @@ def test_merge_kernel_equals_its_torch_specification():
     assert np.array_equal(got.counts, wc.numpy().astype(np.uint64))
     assert np.array_equal(got.keys, wk.numpy().astype(np.uint64))
     assert np.array_equal(got.distances.view(np.uint32), wd.numpy().view(np.uint32))
+
+
+def test_enqueue_then_finish_equals_the_blocking_calls():
+    """usearch_b200_search_many_enqueue x3 + one _finish == three usearch_b200_search_many_device calls, with scratch small
+    enough (test hook) that some queries overflow and have to be retried by _finish."""
+    import subprocess
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import numpy as np, torch, common\n"
+        "from usearch_b200.index import Index\n"
+        "base, q = common.make_collection(6000, 64, 'f32', 384)\n"
+        "ref, blob = common.build_reference_blob(base, 'cos', 'f32', 64, 16, threads=8)\n"
+        "index = Index.restore(blob); index.expansion_search = 64\n"
+        "dev = torch.device('cuda', 0)\n"
+        "qd = torch.from_numpy(q).to(dev)\n"
+        "def bufs(): return (torch.zeros((128, 10), dtype=torch.int64, device=dev), torch.zeros((128, 10), dtype=torch.float32, device=dev), torch.zeros(128, dtype=torch.int32, device=dev))\n"
+        "sync, deferred = [bufs() for _ in range(3)], [bufs() for _ in range(3)]\n"
+        "for i, (k, d, c) in enumerate(sync): index.search_device(qd[i*128:(i+1)*128].data_ptr(), 128, 256, 10, k.data_ptr(), d.data_ptr(), c.data_ptr())\n"
+        "for i, (k, d, c) in enumerate(deferred): index.search_enqueue(qd[i*128:(i+1)*128].data_ptr(), 128, 256, 10, k.data_ptr(), d.data_ptr(), c.data_ptr())\n"
+        "index.search_finish()\n"
+        "torch.cuda.synchronize()\n"
+        "for a, b in zip(sync, deferred):\n"
+        "    assert torch.equal(a[0], b[0]) and torch.equal(a[1].view(torch.int32), b[1].view(torch.int32)) and torch.equal(a[2], b[2])\n"
+        "want = index.search(q, 10)\n"
+        "assert np.array_equal(torch.cat([s[0] for s in deferred]).cpu().numpy().astype(np.uint64), want.keys)\n"
+        "print('ENQUEUE_OK')\n"
+    ) % (common.ROOT, os.path.join(common.ROOT, "tests"))
+    env = dict(os.environ, USEARCH_B200_VISITED="hash", USEARCH_B200_SCRATCH_SHRINK="64")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "ENQUEUE_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]

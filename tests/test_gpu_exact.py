@@ -13,7 +13,10 @@ INDEX_CASES = [
     # metric, scalar, n, d, k, nq, removed
     ("cos", "f32", 5000, 768, 10, 70, 0),
     ("l2sq", "f32", 3000, 97, 33, 64, 100),      # ragged dimension, k > 32, removed members
-    ("ip", "f32", 4096, 128, 256, 17, 0),        # the largest supported k
+    ("ip", "f32", 4096, 128, 256, 17, 0),        # the largest k whose lists live in registers
+    ("l2sq", "f32", 3000, 64, 300, 24, 10),      # count > 256: lists in L2 (tiled scan + exact_merge_big_kernel)
+    ("ip", "i8", 2500, 128, 700, 9, 0),          # count > 256 on i8: the tiled dp4a kernel instead of the IMMA one
+    ("hamming", "b1", 3000, 128, 1000, 5, 0),    # a third of the collection, ties everywhere
     ("cos", "f16", 3000, 256, 10, 64, 50),
     ("l2sq", "bf16", 2000, 100, 10, 64, 0),
     ("ip", "i8", 3000, 1024, 10, 64, 0),

@@ -1,0 +1,9 @@
+#!/bin/bash
+# Round 2, fourth GPU call: full GPU suite with the new kernels, launch-configuration sweeps on the full-size workloads.
+O=gpurun_out/r2c4; mkdir -p $O
+timeout 1500 python -m pytest tests -m gpu -q -x > $O/gpu_suite.log 2>&1; echo "rc=$?" >> $O/gpu_suite.log
+timeout 600 python tools/sweep.py --workload NS --phases --configs "base;prefetch=1;prefetch=1,warps_per_sm=3;warps_per_sm=3" > $O/sweep_ns.jsonl 2> $O/sweep_ns.err
+timeout 600 python tools/sweep.py --workload C3 --steps 4 --configs "base;prefetch=1;stage_sets=2;stage_sets=2,prefetch=1" > $O/sweep_c3.jsonl 2> $O/sweep_c3.err
+timeout 600 python tools/sweep.py --workload C4 --configs "base;prefetch=1;stage_sets=2,prefetch=1" > $O/sweep_c4.jsonl 2> $O/sweep_c4.err
+timeout 900 python tools/sweep.py --workload C5 --n 12500000 --steps 4 --phases --configs "base;prefetch=1" > $O/sweep_c5.jsonl 2> $O/sweep_c5.err
+tail -n 6 $O/gpu_suite.log; for f in ns c3 c4 c5; do echo == $f; tail -n 2 $O/sweep_$f.err; cut -c1-700 $O/sweep_$f.jsonl; done

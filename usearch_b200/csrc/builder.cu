@@ -13,7 +13,7 @@
  *    entry point  moves when the new member's level exceeds the current top                  (:2873-2876)
  *
  *  How a BATCH of new members goes through the same steps here (members of one batch do not see each other — measured to
- *  cost nothing at batches <= 1/16 of the current size):
+ *  cost nothing at batches <= 1/32 of the current size):
  *    1. one launch of the search kernel in INSERT mode (search_kernel.cu): a work item per (member, level), each running
  *       descent + search_to_insert_ on its level -> candidate slots/distances, ascending;
  *    2. link_forward_kernel: a CTA per work item runs refine_ (the lazy sequential heuristic, evaluated for all kept
@@ -701,7 +701,7 @@ char const* frozen_index_t::add_many(uint64_t const* new_keys, void const* vecto
 
     /* link them, batch by batch */
     static size_t const batch_max = [] { char const* v = std::getenv("USEARCH_B200_BUILD_BATCH"); return v && std::atol(v) > 0 ? (size_t)std::atol(v) : (size_t)32768; }();
-    static size_t const ratio = [] { char const* v = std::getenv("USEARCH_B200_BUILD_RATIO"); return v && std::atol(v) > 0 ? (size_t)std::atol(v) : (size_t)16; }();
+    static size_t const ratio = [] { char const* v = std::getenv("USEARCH_B200_BUILD_RATIO"); return v && std::atol(v) > 0 ? (size_t)std::atol(v) : (size_t)32; }();
     size_t at = first;
     while (at < size) {
         if (d.n == 0) { /* the first member: entry point, no links (index.hpp:2836-2841) */

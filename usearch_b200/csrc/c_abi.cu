@@ -345,6 +345,25 @@ void usearch_b200_search_many_device(usearch_index_t index, void const* queries,
                                        computed_distances, visited_members, s));
 }
 
+/* the asynchronous pair: enqueue any number of batches (kernel launches only, nothing waits), then finish once */
+void usearch_b200_search_many_enqueue(usearch_index_t index, void const* queries, size_t queries_count, size_t queries_stride,
+                                      size_t count, usearch_key_t* keys, usearch_distance_t* distances, uint32_t* counts,
+                                      uint32_t* computed_distances, uint32_t* visited_members, void* cuda_stream,
+                                      usearch_error_t* error) {
+    frozen_index_t* ix = as_index(index);
+    std::lock_guard<std::mutex> lock(ix->mutex);
+    if (char const* e = ix->ensure_context()) return set_error(error, e);
+    cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ix->stream;
+    set_error(error, ix->search_device(queries, queries_count, queries_stride, count, keys, distances, counts, computed_distances,
+                                       visited_members, s, true));
+}
+
+void usearch_b200_search_many_finish(usearch_index_t index, usearch_error_t* error) {
+    frozen_index_t* ix = as_index(index);
+    std::lock_guard<std::mutex> lock(ix->mutex);
+    set_error(error, ix->search_finish());
+}
+
 /* c/lib.cpp:378-386 -> index_dense_gt::add (index_dense.hpp:760-765, :2002-2050). One member per call goes through the same
  * batched builder as usearch_b200_add_many (a batch of one): correct, but the throughput entry is the batch call. */
 void usearch_add(usearch_index_t index, usearch_key_t key, void const* vector, usearch_scalar_kind_t kind, usearch_error_t* error) {
@@ -522,6 +541,17 @@ void usearch_b200_profile_phases(usearch_index_t index, int enable, uint64_t* co
     }
     ix->profile_phases = enable != 0;
     if (ix->profile_phases && !ix->phase_cycles.reserve(16)) cudaMemset(ix->phase_cycles.ptr, 0, 128);
+}
+
+int usearch_b200_tune(usearch_index_t index, char const* knob, int value) {
+    frozen_index_t* ix = as_index(index);
+    std::lock_guard<std::mutex> lock(ix->mutex);
+    if (!std::strcmp(knob, "stage_sets")) ix->tune.stage_sets = value;
+    else if (!std::strcmp(knob, "warps_per_sm")) ix->tune.warps_per_sm = value;
+    else if (!std::strcmp(knob, "issue_per_lane")) ix->tune.issue_per_lane = value;
+    else if (!std::strcmp(knob, "prefetch")) ix->tune.prefetch = value;
+    else return -1;
+    return 0;
 }
 
 int usearch_b200_device(usearch_index_t index) { return as_index(index)->device; }

@@ -331,6 +331,40 @@ __global__ void exact_merge_kernel(device_index_t ix, exact_args_t a) {
     if (lane == 0) a.out_counts[qi] = top_size;
 }
 
+/* the same merge for count > 256: the merged list lives in global memory (L2) instead of registers */
+__global__ void exact_merge_big_kernel(device_index_t ix, exact_args_t a, float* merged_d, uint32_t* merged_s) {
+    uint32_t const qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int const lane = threadIdx.x & 31;
+    if (qi >= a.nq) return;
+    float* md = merged_d + (size_t)qi * a.k;
+    uint32_t* ms = merged_s + (size_t)qi * a.k;
+    uint32_t top_size = 0;
+    float worst = 0.f;
+    for (uint32_t seg = 0; seg < a.segments; ++seg) {
+        uint32_t const n = a.part_n[(size_t)qi * a.segments + seg];
+        size_t const row = ((size_t)qi * a.segments + seg) * a.k;
+        for (uint32_t i = 0; i < n; ++i) {
+            float const cd = a.part_d[row + i];
+            if (top_size == a.k && cd > worst) break; /* the segment's list is ascending: nothing later can enter */
+            top_insert_global_keyed(md, ms, top_size, a.k, cd, a.part_s[row + i], lane);
+            if (top_size == a.k) worst = reinterpret_cast<float volatile*>(md)[a.k - 1];
+        }
+    }
+    __syncwarp();
+    for (uint32_t i = lane; i < a.k; i += 32) {
+        uint64_t key = 0;
+        uint32_t bits = SNAN_BITS;
+        if (i < top_size) {
+            uint32_t const slot = reinterpret_cast<uint32_t volatile*>(ms)[i];
+            key = a.slots_as_keys ? (uint64_t)slot : ix.keys[slot];
+            bits = __float_as_uint(reinterpret_cast<float volatile*>(md)[i]);
+        }
+        a.out_keys[(size_t)qi * a.k + i] = key;
+        reinterpret_cast<uint32_t*>(a.out_dists)[(size_t)qi * a.k + i] = bits;
+    }
+    if (lane == 0) a.out_counts[qi] = top_size;
+}
+
 template <class M> static cudaError_t exact_launch_t(device_index_t const& ix, exact_args_t const& a, bool swap, dim3 grid, size_t smem,
                                                      cudaStream_t stream) {
     if (swap) {
@@ -379,7 +413,9 @@ char const* exact_search_device(device_index_t const& ix, int sm_count, void con
                                 bool swap, bool slots_as_keys, uint64_t* d_keys, float* d_dists, uint32_t* d_counts,
                                 device_buffer_t<uint8_t>& scratch, cudaStream_t stream) {
     if (!nq || !k) return nullptr;
-    if (k > 32 * TOP_E) return "Exact search offload supports count <= 256";
+    /* count <= 256: k-best lists in registers (scan, IMMA, merge); beyond that the tiled kernel's global-memory lists and
+     * exact_merge_big_kernel carry any count (search_exact_ takes any `wanted`, index.hpp:4251-4268) */
+    bool const big_k = k > 32 * TOP_E;
     if (!ix.n) { /* nothing to scan: empty rows */
         if (cudaMemsetAsync(d_counts, 0, nq * 4, stream) != cudaSuccess) return "CUDA failure: memset";
         if (cudaMemsetAsync(d_keys, 0, nq * k * 8, stream) != cudaSuccess) return "CUDA failure: memset";
@@ -402,10 +438,11 @@ char const* exact_search_device(device_index_t const& ix, int sm_count, void con
         return !v ? 0 : (std::strcmp(v, "scan") == 0 ? 1 : (std::strcmp(v, "tiled") == 0 ? 2 : (std::strcmp(v, "imma") == 0 ? 3 : 0)));
     }();
     /* i8: integer sums are order independent, the tensor cores give the reference's bits (exact_imma.cu) */
-    bool const imma = ix.scalar == SCALAR_I8 && (forced == 0 || forced == 3) &&
+    bool const imma = !big_k && ix.scalar == SCALAR_I8 && (forced == 0 || forced == 3) &&
                       (ix.metric == METRIC_IP || ix.metric == METRIC_L2SQ || ix.metric == METRIC_COS);
     if (forced == 3 && !imma) return "The IMMA exact-search kernel serves i8 vectors only";
-    bool const tiled = !imma && (forced == 1 ? false : tiled_smem <= 227 * 1024);
+    bool const tiled = !imma && (forced == 1 && !big_k ? false : tiled_smem <= 227 * 1024);
+    if (big_k && !tiled) return "Exact search with count > 256 needs vectors that fit the tiled stage";
     if (forced == 2 && !tiled) return "Vectors too long for the tiled exact-search stage";
     int const vpp = imma ? exact_imma_tile_vectors() : (tiled ? tile_vectors : 32 / lpv); /* vectors per tile */
     uint32_t const qpc = imma ? (uint32_t)exact_imma_tile_queries() : (tiled ? (uint32_t)qpc_tiled : (uint32_t)EXACT_WARPS);
@@ -441,7 +478,7 @@ char const* exact_search_device(device_index_t const& ix, int sm_count, void con
     size_t const rows = nq * segments;
     size_t const lists = rows * k * 8 + rows * 4;
     size_t const norms_at = (lists + 15) / 16 * 16;
-    size_t const need = norms_at + (imma ? (nq + (size_t)ix.n) * 4 : 0) + 64;
+    size_t const need = norms_at + (imma ? (nq + (size_t)ix.n) * 4 : 0) + (big_k ? nq * k * 8 : 0) + 64;
     if (char const* e = scratch.reserve(need)) return e;
     a.part_d = reinterpret_cast<float*>(scratch.ptr);
     a.part_s = reinterpret_cast<uint32_t*>(scratch.ptr + rows * k * 4);
@@ -490,7 +527,12 @@ char const* exact_search_device(device_index_t const& ix, int sm_count, void con
     default: break;
     }
     if (e != cudaSuccess) return "CUDA failure: exact scan launch";
-    exact_merge_kernel<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, stream>>>(ix, a);
+    if (big_k) {
+        float* merged_d = reinterpret_cast<float*>(scratch.ptr + norms_at);
+        exact_merge_big_kernel<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, stream>>>(ix, a, merged_d,
+                                                                                      reinterpret_cast<uint32_t*>(merged_d + nq * k));
+    } else
+        exact_merge_kernel<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, stream>>>(ix, a);
     if (cudaGetLastError() != cudaSuccess) return "CUDA failure: exact merge launch";
     return nullptr;
 }

@@ -61,6 +61,8 @@ size_t bits_per_scalar(uint32_t s) { /* index_plugins.hpp:237-257 */
 }
 
 frozen_index_t::~frozen_index_t() {
+    for (pending_search_t& p : pending) pending_free.push_back(p.status);
+    for (device_buffer_t<uint32_t>* b : pending_free) { b->release(); delete b; }
     leave_shards();
     release_device();
     if (stream) cudaStreamDestroy(stream);
@@ -432,7 +434,7 @@ char const* frozen_index_t::plan(uint32_t k, uint32_t visited_cap_override, laun
     /* an SM has 228 KB of shared memory and charges 1 KB per resident CTA on top of its request */
     size_t const smem_sm = 228 * 1024, cta_tax = 1024, smem_cta_max = 227 * 1024;
     uint32_t const min_heap = 128 * 8;
-    static int const forced_sets = [] { char const* v = std::getenv("USEARCH_B200_STAGE_SETS"); return v ? std::atoi(v) : 0; }();
+    int const forced_sets = tune.stage_sets;
     static int const forced_segs = [] { char const* v = std::getenv("USEARCH_B200_STAGE_SEGMENTS"); return v ? std::atoi(v) : 0; }();
     pl.stage_sets = 1;
     pl.stage_segments = 1;
@@ -463,7 +465,7 @@ char const* frozen_index_t::plan(uint32_t k, uint32_t visited_cap_override, laun
     pl.off_heap = off;
     uint32_t const fixed = off;
     if (fixed + min_heap > smem_cta_max) return "Expansion or dimensionality too large for on-chip state";
-    static int const forced_warps = [] { char const* v = std::getenv("USEARCH_B200_WARPS_PER_SM"); return v ? std::atoi(v) : 0; }();
+    int const forced_warps = tune.warps_per_sm;
     uint32_t warps_sm = (uint32_t)std::min<size_t>(smem_sm / (fixed + min_heap + cta_tax), (size_t)search_max_warps_per_sm(d));
     if (forced_warps > 0) warps_sm = std::min<uint32_t>(warps_sm, (uint32_t)forced_warps);
     warps_sm = std::max(warps_sm, 1u);
@@ -556,14 +558,14 @@ char const* frozen_index_t::prepare_launch(launch_plan_t const& pl, size_t warps
     a.stage_segments = pl.stage_segments;
     a.stage_seg_chunks = pl.stage_seg_chunks;
     /* measured on B200 (1M x 768 f32): per-lane issue 9.67 ms, single-lane back-to-back issue 10.33 ms */
-    static int const issue_per_lane = [] { char const* v = std::getenv("USEARCH_B200_ISSUE_PER_LANE"); return v ? std::atoi(v) : 1; }();
-    a.issue_per_lane = (uint32_t)issue_per_lane;
+    a.issue_per_lane = (uint32_t)tune.issue_per_lane;
+    a.prefetch_next = (uint32_t)tune.prefetch;
     return nullptr;
 }
 
 char const* frozen_index_t::search_device(void const* d_queries, size_t nq, size_t stride, size_t k, uint64_t* d_keys,
                                           float* d_dists, uint32_t* d_counts, uint32_t* d_computed, uint32_t* d_cycles,
-                                          cudaStream_t s) {
+                                          cudaStream_t s, bool defer) {
     if (nq == 0 || k == 0) return nullptr;
     if (nq > 0x7FFFFFFFull) return "Too many queries in one batch";
     if (char const* e = ensure_context()) return e;
@@ -578,8 +580,19 @@ char const* frozen_index_t::search_device(void const* d_queries, size_t nq, size
     int blocks = (int)std::min<size_t>((size_t)pl.blocks, (nq + wpb - 1) / wpb);
     size_t warps = (size_t)blocks * wpb;
 
-    if (char const* e = status.reserve(nq)) return e;
     if (char const* e = h_status.reserve(nq)) return e;
+    uint32_t* status_ptr = nullptr;
+    if (defer) { /* every batch in flight owns its status words until search_finish has looked at them */
+        if (pending_free.empty()) pending_free.emplace_back(new device_buffer_t<uint32_t>());
+        device_buffer_t<uint32_t>* buf = pending_free.back();
+        pending_free.pop_back();
+        if (char const* e = buf->reserve(nq)) { pending_free.push_back(buf); return e; }
+        pending.push_back(pending_search_t{buf, search_args_t{}, pl.maxed, s});
+        status_ptr = buf->ptr;
+    } else {
+        if (char const* e = status.reserve(nq)) return e;
+        status_ptr = status.ptr;
+    }
     search_args_t a;
     if (char const* e = prepare_launch(pl, warps, a, s)) return e;
     a.queries = static_cast<uint8_t const*>(d_queries);
@@ -591,7 +604,7 @@ char const* frozen_index_t::search_device(void const* d_queries, size_t nq, size
     a.out_counts = d_counts;
     a.out_computed = d_computed;
     a.out_visited = d_cycles;
-    a.status = status.ptr;
+    a.status = status_ptr;
     a.allow_bits = active_allow_bits;
     a.cluster_end_level = active_cluster_end_level;
 
@@ -604,16 +617,41 @@ char const* frozen_index_t::search_device(void const* d_queries, size_t nq, size
     CU(search_launch(d, a, blocks, pl.smem_per_block, s));
     CU(cudaEventRecord(ev_end, s));
     kernel_launches += 1;
+    if (defer) { /* enqueue only: search_finish synchronises, looks at the status words and retries what overflowed */
+        pending.back().args = a;
+        return nullptr;
+    }
     CU(cudaMemcpyAsync(h_status.ptr, status.ptr, nq * 4, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     CU(cudaEventElapsedTime(&last_kernel_ms, ev_begin, ev_end));
+    return retry_overflowed(a, pl.maxed, s);
+}
 
-    /* scratch overflow: rerun just those queries with 8x larger tables until they fit */
+/* every deferred batch: wait, then give the queries whose scratch overflowed their retry */
+char const* frozen_index_t::search_finish() {
+    char const* first_error = nullptr;
+    for (pending_search_t& p : pending) {
+        char const* e = cuda_error(cudaStreamSynchronize(p.stream));
+        if (!e) e = h_status.reserve(p.args.nq);
+        if (!e) e = cuda_error(cudaMemcpy(h_status.ptr, p.status->ptr, (size_t)p.args.nq * 4, cudaMemcpyDeviceToHost));
+        if (!e) e = retry_overflowed(p.args, p.maxed, p.stream);
+        if (e && !first_error) first_error = e;
+        pending_free.push_back(p.status);
+    }
+    pending.clear();
+    if (ev_begin && ev_end && !first_error) cudaEventElapsedTime(&last_kernel_ms, ev_begin, ev_end);
+    return first_error;
+}
+
+/* scratch overflow (h_status holds the status words of the launch described by `a`): rerun just those queries with 8x
+ * larger tables until they fit */
+char const* frozen_index_t::retry_overflowed(search_args_t const& a, bool maxed, cudaStream_t s) {
+    size_t const nq = a.nq, k = a.k;
+    int const wpb = search_warps_per_block();
     std::vector<uint32_t> failed;
     for (size_t i = 0; i < nq; ++i)
         if (h_status.ptr[i] != STATUS_OK) failed.push_back((uint32_t)i);
     uint64_t scale = 1;
-    bool maxed = pl.maxed;
     while (!failed.empty()) {
         if (maxed) return "Search scratch overflow that full-size scratch could not fix";
         scale *= 8;
@@ -638,7 +676,7 @@ char const* frozen_index_t::search_device(void const* d_queries, size_t nq, size
         CU(cudaMemsetAsync(work_counter.ptr, 0, 8, s));
         CU(search_launch(d, r, rblocks, rp.smem_per_block, s));
         kernel_launches += 1;
-        CU(cudaMemcpyAsync(h_status.ptr, status.ptr, nq * 4, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(h_status.ptr, a.status, nq * 4, cudaMemcpyDeviceToHost, s));
         CU(cudaStreamSynchronize(s));
         std::vector<uint32_t> still;
         for (uint32_t qi : failed)

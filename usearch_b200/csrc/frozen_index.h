@@ -199,6 +199,19 @@ struct frozen_index_t {
     bool loaded = false;
     void* dev_allocs[8] = {nullptr};
 
+    /* tuning knobs of the search launch: environment at construction (USEARCH_B200_STAGE_SETS, _WARPS_PER_SM,
+     * _ISSUE_PER_LANE, _PREFETCH), changeable per handle with usearch_b200_tune (bench sweeps, tests) */
+    struct tune_t {
+        int stage_sets = env_int("USEARCH_B200_STAGE_SETS", 0);     /* 0 = planned, 1 or 2 = forced */
+        int warps_per_sm = env_int("USEARCH_B200_WARPS_PER_SM", 0); /* 0 = as many as fit, else an upper bound */
+        int issue_per_lane = env_int("USEARCH_B200_ISSUE_PER_LANE", 1);
+        int prefetch = env_int("USEARCH_B200_PREFETCH", 0);
+        static int env_int(char const* name, int fallback) {
+            char const* v = std::getenv(name);
+            return v ? std::atoi(v) : fallback;
+        }
+    } tune;
+
     /* per-handle execution context */
     std::mutex mutex;
     cudaStream_t stream = nullptr;
@@ -258,7 +271,13 @@ struct frozen_index_t {
     char const* plan(uint32_t k, uint32_t visited_cap_override, launch_plan_t& plan, uint32_t ef_override = 0) const;
     char const* prepare_launch(launch_plan_t const& pl, size_t warps, search_args_t& a, cudaStream_t s);
     char const* search_device(void const* d_queries, size_t nq, size_t stride, size_t k, uint64_t* d_keys, float* d_dists,
-                              uint32_t* d_counts, uint32_t* d_computed, uint32_t* d_cycles, cudaStream_t stream);
+                              uint32_t* d_counts, uint32_t* d_computed, uint32_t* d_cycles, cudaStream_t stream, bool defer = false);
+    /* deferred launches (usearch_b200_search_many_enqueue): status words and arguments kept until search_finish */
+    struct pending_search_t { device_buffer_t<uint32_t>* status; search_args_t args; bool maxed; cudaStream_t stream; };
+    std::vector<pending_search_t> pending;
+    std::vector<device_buffer_t<uint32_t>*> pending_free;
+    char const* search_finish();
+    char const* retry_overflowed(search_args_t const& a, bool maxed, cudaStream_t stream);
     /* usearch_search from many host threads: callers that arrive while a launch is in flight are gathered and served by
      * ONE launch (a leader runs the batch, the others wait for their rows) — the reference serves them from distinct
      * thread contexts in parallel (index.hpp:3033-3039, index_dense.hpp:1984-2000) */

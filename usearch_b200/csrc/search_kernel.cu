@@ -39,6 +39,7 @@ namespace usearch_b200 {
 
 constexpr int THREADS = 32; /* one warp per CTA: warps never synchronise with each other */
 constexpr int LOADS_IN_FLIGHT = 8;
+constexpr int BATCH_LOADS = 4; /* 16-byte loads a lane keeps in flight across passes in measure_direct_batched */
 
 __device__ __forceinline__ uint32_t hash_slot(uint32_t s) { return s * 0x9E3779B1u; }
 
@@ -237,6 +238,48 @@ struct warp_ctx_t {
 
 /* ---- distances of a whole candidate list ---------------------------------------------------- */
 
+/*
+ *  DIRECT, short vectors: a lane's share of a vector is CPL <= 2 chunks, so the loads of BATCH_LOADS / CPL PASSES (each pass = 32 / LPV
+ *  candidates) are issued together before any of them is consumed: a whole list of 128 binary codes of 256 bits
+ *  (BASELINE config C5: LPV 2, CPL 1) costs two memory round trips instead of eight (more loads in flight would spill: the caller keeps ~110 registers live).
+ */
+template <class M, int CPL>
+__device__ __noinline__ void measure_direct_batched(device_index_t const& ix, warp_ctx_t& w, typename M::qconst_t qc,
+                                                       uint32_t ncand, int lane) {
+    constexpr int LPV = M::LPV, VPP = 32 / LPV, PB = BATCH_LOADS / CPL;
+    int const g = lane / LPV, sub = lane % LPV;
+    uint32_t const chunks = ix.chunks16;
+    for (uint32_t base = 0; base < ncand; base += VPP * PB) {
+        uint4 r[PB][CPL];
+#pragma unroll
+        for (int p = 0; p < PB; ++p) {
+            uint32_t const c = base + (uint32_t)(p * VPP + g);
+            uint32_t const slot = c < ncand ? w.cand_s[c] : 0u;
+            uint4 const* v = reinterpret_cast<uint4 const*>(ix.vectors + (size_t)slot * ix.vec_stride);
+#pragma unroll
+            for (int i = 0; i < CPL; ++i) {
+                uint32_t const j = (uint32_t)(sub + i * LPV);
+                if (c < ncand && j < chunks) r[p][i] = ldg_stream(v + j);
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < PB; ++p) {
+            uint32_t const c = base + (uint32_t)(p * VPP + g);
+            if (base + (uint32_t)(p * VPP) >= ncand) break; /* uniform: no candidate in this pass */
+            typename M::acc_t acc;
+            M::init(acc);
+#pragma unroll
+            for (int i = 0; i < CPL; ++i) {
+                uint32_t const j = (uint32_t)(sub + i * LPV);
+                if (c < ncand && j < chunks) M::step(acc, r[p][i], w.q4[j]);
+            }
+            float const d = M::finish(acc, qc); /* shuffles inside the lane group: executed by every lane */
+            if (c < ncand && sub == 0) w.cand_d[c] = d;
+        }
+    }
+    __syncwarp();
+}
+
 /* DIRECT: 16-byte chunks straight from HBM into registers, LOADS_IN_FLIGHT per lane. */
 template <class M>
 __device__ __noinline__ void measure_direct(device_index_t const& ix, warp_ctx_t& w, typename M::qconst_t qc,
@@ -244,6 +287,9 @@ __device__ __noinline__ void measure_direct(device_index_t const& ix, warp_ctx_t
     constexpr int LPV = M::LPV, VPP = 32 / LPV;
     int const g = lane / LPV, sub = lane % LPV;
     uint32_t const chunks = ix.chunks16;
+    uint32_t const cpl = (chunks + LPV - 1) / LPV; /* chunks per lane */
+    if (cpl == 1) return measure_direct_batched<M, 1>(ix, w, qc, ncand, lane);
+    if (cpl == 2) return measure_direct_batched<M, 2>(ix, w, qc, ncand, lane);
     for (uint32_t base = 0; base < ncand; base += VPP) {
         uint32_t c = base + g;
         bool act = c < ncand;
@@ -543,6 +589,10 @@ __device__ __forceinline__ void search_one(device_index_t const& ix, search_args
         heap_size = cluster ? 0 : 1;
         visited_count = cluster ? 0 : 1;
         uint32_t pre_node = EMPTY_SLOT, pre_s0 = EMPTY_SLOT, pre_s1 = EMPTY_SLOT; /* speculative row prefetch */
+        /* DIRECT kernels (short vectors, binary codes) have registers to spare and hops so short that the list itself is
+         * the critical path: they keep rows of up to 128 neighbours (M = 64, BASELINE config C5) in registers as well */
+        constexpr bool WIDE = !STAGED;
+        uint32_t pre_s2 = EMPTY_SLOT, pre_s3 = EMPTY_SLOT;
         PHASE(pc0)
         {
             /* cluster(): the closest member at that level is the whole answer, predicate ignored (index.hpp:3122) */
@@ -561,22 +611,31 @@ __device__ __forceinline__ void search_one(device_index_t const& ix, search_args
             if (cur.d > radius && top_size == ef) break;
             /* the neighbour row is addressed by the root alone: fetch it while lane 0 sifts the heap */
             uint32_t const* row = row_of(cur.s);
-            uint32_t s0, s1;
+            uint32_t s0, s1, s2 = EMPTY_SLOT, s3 = EMPTY_SLOT;
             if (cur.s == pre_node) { /* the row was prefetched during the previous hop */
                 s0 = pre_s0;
                 s1 = pre_s1;
+                if constexpr (WIDE) { s2 = pre_s2; s3 = pre_s3; }
             } else {
                 s0 = lane < (int)width ? __ldg(row + lane) : EMPTY_SLOT;
                 s1 = lane + 32 < (int)width ? __ldg(row + lane + 32) : EMPTY_SLOT;
+                if constexpr (WIDE) {
+                    s2 = lane + 64 < (int)width ? __ldg(row + lane + 64) : EMPTY_SLOT;
+                    s3 = lane + 96 < (int)width ? __ldg(row + lane + 96) : EMPTY_SLOT;
+                }
             }
             __syncwarp(); /* every lane holds `cur` before lane 0 rearranges the heap */
             /* BITMAP visits: one atomicOr per neighbour, all in flight together (the frozen lists hold no
              * duplicates and no self-links: those can never be `fresh`, freeze drops them). They are issued
              * BEFORE the pop so that lane 0 sifts the heap while the atomics make their round trip to L2. */
-            uint32_t o0 = 0xFFFFFFFFu, o1 = 0xFFFFFFFFu;
+            uint32_t o0 = 0xFFFFFFFFu, o1 = 0xFFFFFFFFu, o2 = 0xFFFFFFFFu, o3 = 0xFFFFFFFFu;
             if (bitmap) {
                 if (s0 != EMPTY_SLOT) o0 = atomicOr(&visited[s0 >> 5], 1u << (s0 & 31));
                 if (s1 != EMPTY_SLOT) o1 = atomicOr(&visited[s1 >> 5], 1u << (s1 & 31));
+                if constexpr (WIDE) {
+                    if (s2 != EMPTY_SLOT) o2 = atomicOr(&visited[s2 >> 5], 1u << (s2 & 31));
+                    if (s3 != EMPTY_SLOT) o3 = atomicOr(&visited[s3 >> 5], 1u << (s3 & 31));
+                }
             }
             if (!heap.pop_warp(heap_size, lane)) {
                 if (lane == 0) heap.pop(heap_size);
@@ -591,6 +650,10 @@ __device__ __forceinline__ void search_one(device_index_t const& ix, search_args
                 uint32_t const* next_row = row_of(pre_node);
                 pre_s0 = lane < (int)width ? __ldg(next_row + lane) : EMPTY_SLOT;
                 pre_s1 = lane + 32 < (int)width ? __ldg(next_row + lane + 32) : EMPTY_SLOT;
+                if constexpr (WIDE) {
+                    pre_s2 = lane + 64 < (int)width ? __ldg(next_row + lane + 64) : EMPTY_SLOT;
+                    pre_s3 = lane + 96 < (int)width ? __ldg(next_row + lane + 96) : EMPTY_SLOT;
+                }
             } else
                 pre_node = EMPTY_SLOT;
             PHASE(pc1)
@@ -613,7 +676,20 @@ __device__ __forceinline__ void search_one(device_index_t const& ix, search_args
                         if (f1) vlog[visited_count + __popc(bal0) + __popc(bal1 & lt)] = s1;
                     }
                 }
-                for (uint32_t b = 64; b < width; b += 32) {
+                if constexpr (WIDE) { /* neighbours 64..127, already in registers */
+                    bool const f2 = s2 != EMPTY_SLOT && !((o2 >> (s2 & 31)) & 1u);
+                    bool const f3 = s3 != EMPTY_SLOT && !((o3 >> (s3 & 31)) & 1u);
+                    uint32_t const bal2 = __ballot_sync(0xffffffffu, f2), bal3 = __ballot_sync(0xffffffffu, f3);
+                    uint32_t const at2 = ncand + __popc(bal2 & lt), at3 = ncand + __popc(bal2) + __popc(bal3 & lt);
+                    if (f2) cand_s[at2] = s2;
+                    if (f3) cand_s[at3] = s3;
+                    if (logged && !log_overflow) {
+                        if (f2) vlog[visited_count + at2] = s2;
+                        if (f3) vlog[visited_count + at3] = s3;
+                    }
+                    ncand += __popc(bal2) + __popc(bal3);
+                }
+                for (uint32_t b = WIDE ? 128 : 64; b < width; b += 32) {
                     uint32_t i = b + lane;
                     uint32_t s = i < width ? __ldg(row + i) : EMPTY_SLOT;
                     uint32_t o = s != EMPTY_SLOT ? atomicOr(&visited[s >> 5], 1u << (s & 31)) : 0xFFFFFFFFu;
@@ -628,7 +704,7 @@ __device__ __forceinline__ void search_one(device_index_t const& ix, search_args
                 if ((visited_count + width) * 2 > a.visited_cap) { status = STATUS_VISITED_OVERFLOW; break; }
                 for (uint32_t b = 0; b < width; b += 32) {
                     uint32_t i = b + lane;
-                    uint32_t s = b == 0 ? s0 : (b == 32 ? s1 : (i < width ? __ldg(row + i) : EMPTY_SLOT));
+                    uint32_t s = b == 0 ? s0 : (b == 32 ? s1 : (WIDE && b == 64 ? s2 : (WIDE && b == 96 ? s3 : (i < width ? __ldg(row + i) : EMPTY_SLOT))));
                     bool fresh = false;
                     if (s != EMPTY_SLOT) {
                         uint32_t h = hash_slot(s) & vmask;
@@ -651,6 +727,19 @@ __device__ __forceinline__ void search_one(device_index_t const& ix, search_args
 
             measure_list<M, STAGED>(ix, a, w, qc, ncand, lane);
             computed += ncand;
+            /* Speculation, one step further than the row prefetch: the accept replay below, the pop and the visited
+             * round trip of the next hop keep this warp off the memory system for a microsecond or two. Unless this
+             * hop found something closer, `pre_node` is expanded next: ask L2 for those of its neighbours whose bit
+             * is still clear (a plain read of the bitmap word; nothing is marked). A wrong guess costs bandwidth, never
+             * correctness. */
+            if (a.prefetch_next && bitmap && pre_node != EMPTY_SLOT) {
+                uint32_t const w0 = pre_s0 != EMPTY_SLOT ? ld_l2_u32(&visited[pre_s0 >> 5]) : 0xFFFFFFFFu;
+                uint32_t const w1 = pre_s1 != EMPTY_SLOT ? ld_l2_u32(&visited[pre_s1 >> 5]) : 0xFFFFFFFFu;
+                if (pre_s0 != EMPTY_SLOT && !((w0 >> (pre_s0 & 31)) & 1u))
+                    bulk_prefetch_l2(ix.vectors + (size_t)pre_s0 * ix.vec_stride, (uint32_t)ix.vec_stride);
+                if (pre_s1 != EMPTY_SLOT && !((w1 >> (pre_s1 & 31)) & 1u))
+                    bulk_prefetch_l2(ix.vectors + (size_t)pre_s1 * ix.vec_stride, (uint32_t)ix.vec_stride);
+            }
             PHASE(pc4)
 
             /* The reference's sequential accept loop, replayed in stored order. `radius` only shrinks

@@ -53,6 +53,7 @@ EXPORTED_SYMBOLS = [
     "usearch_b200_bytes_per_vector", "usearch_b200_max_level", "usearch_b200_add_many", "usearch_b200_add_many_device",
     "usearch_b200_shards_unique_id", "usearch_b200_shards_join", "usearch_b200_sharded_search_many",
     "usearch_b200_sharded_search_many_device", "usearch_b200_shards_payload_bytes", "usearch_b200_merge_topk",
+    "usearch_b200_search_many_enqueue", "usearch_b200_search_many_finish", "usearch_b200_tune",
 ]
 
 
@@ -98,6 +99,10 @@ def load_library() -> C.CDLL:
     lib.usearch_b200_search_many_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t,
                                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                     C.c_void_p, err]
+    lib.usearch_b200_search_many_enqueue.argtypes = lib.usearch_b200_search_many_device.argtypes
+    lib.usearch_b200_search_many_finish.argtypes = [C.c_void_p, err]
+    lib.usearch_b200_tune.restype = C.c_int
+    lib.usearch_b200_tune.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     lib.usearch_b200_filtered_search_many.restype = C.c_size_t
     lib.usearch_b200_filtered_search_many.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int,
                                                       C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
@@ -495,6 +500,12 @@ class Index:
             return Matches(keys[0, :n], distances[0, :n], vm, cd)
         return BatchMatches(keys, distances, counts, vm, cd)
 
+    def tune(self, **knobs: int) -> None:
+        """Launch tuning knobs of this handle (stage_sets, warps_per_sm, issue_per_lane, prefetch); results never change."""
+        for name, value in knobs.items():
+            if self._lib.usearch_b200_tune(self._h, name.encode(), int(value)) != 0:
+                raise ValueError(f"unknown knob {name}")
+
     def profile_phases(self, enable: bool = True) -> dict:
         """Read (then reset) the kernel's per-phase cycle counters; see include/usearch_b200.h."""
         out = np.zeros(16, dtype=np.uint64)
@@ -536,6 +547,20 @@ class Index:
         self._lib.usearch_b200_sharded_search_many_device(self._h, queries_ptr, nq, stride, count, keys_ptr, distances_ptr,
                                                           counts_ptr, computed_ptr or None, visited_ptr or None,
                                                           stream or None, C.byref(err))
+        _raise(err)
+
+    def search_enqueue(self, queries_ptr: int, nq: int, stride: int, count: int, keys_ptr: int, distances_ptr: int,
+                       counts_ptr: int, computed_ptr: int = 0, visited_ptr: int = 0, stream: int = 0) -> None:
+        """Like :meth:`search_device` but returns as soon as the kernel is enqueued; call :meth:`search_finish` once."""
+        err = C.c_char_p()
+        self._lib.usearch_b200_search_many_enqueue(self._h, queries_ptr, nq, stride, count, keys_ptr, distances_ptr,
+                                                   counts_ptr, computed_ptr or None, visited_ptr or None,
+                                                   stream or None, C.byref(err))
+        _raise(err)
+
+    def search_finish(self) -> None:
+        err = C.c_char_p()
+        self._lib.usearch_b200_search_many_finish(self._h, C.byref(err))
         _raise(err)
 
     def search_device(self, queries_ptr: int, nq: int, stride: int, count: int, keys_ptr: int, distances_ptr: int,
