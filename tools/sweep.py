@@ -1,6 +1,6 @@
 """Build one bench workload on the GPU, then time the search kernel under several launch configurations in ONE process.
 
-    python tools/sweep.py --workload NS --configs "base;prefetch=1;prefetch=1,warps_per_sm=3" --steps 6
+    python tools/sweep.py --workload NS --configs "base;stage_copy=1;stage_copy=1,warps_per_sm=3" --steps 6
 
 Prints one JSON line per configuration: kernel ms per launch (CUDA events inside the library), algorithmic GB/s and the
 fraction of the measured HBM peak (the roofline figure of bench.py), recall on the first batch."""
@@ -59,7 +59,7 @@ def main():
     m0 = 2 * index.connectivity
     print(json.dumps({"workload": bench.workload_name(a), "build_s": round(build_s, 1), "hbm_gb": round(index.memory_usage / 1e9, 2)}), flush=True)
     for spec in o.configs.split(";"):
-        knobs = {"stage_sets": 0, "warps_per_sm": 0, "issue_per_lane": 1, "prefetch": 0}
+        knobs = {"stage_sets": 0, "warps_per_sm": 0, "issue_per_lane": 1, "stage_copy": 0, "dense_direct": 0}
         if spec != "base":
             for kv in spec.split(","):
                 name, value = kv.split("=")

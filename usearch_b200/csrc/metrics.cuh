@@ -44,6 +44,39 @@ template <int LPV> __device__ __forceinline__ int reduce_add_i32(int v) {
     return v;
 }
 
+/* ---- packed f32 pairs: Blackwell issues two IEEE fma.rn.f32 in one FFMA2 -------------------- */
+/*
+ *  `fma.rn.f32x2` / `sub.rn.f32x2` (sm_100: SASS FFMA2 / FADD2) apply the scalar round-to-nearest operation to both halves
+ *  of a 64-bit register pair. Every accumulator still sees the same operands in the same order, so the sums keep the bits
+ *  of the scalar chains they replace (asserted by every parity test); the hot loops issue half as many FP instructions.
+ */
+__device__ __forceinline__ unsigned long long pack2(uint32_t lo, uint32_t hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+__device__ __forceinline__ unsigned long long pack2f(float lo, float hi) { return pack2(__float_as_uint(lo), __float_as_uint(hi)); }
+__device__ __forceinline__ void unpack2f(unsigned long long v, float& lo, float& hi) {
+    uint32_t a, b;
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(a), "=r"(b) : "l"(v));
+    lo = __uint_as_float(a);
+    hi = __uint_as_float(b);
+}
+__device__ __forceinline__ void fma2(unsigned long long& acc, unsigned long long a, unsigned long long b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ unsigned long long sub2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+/* the four accumulators of a lane as two pairs <-> float[4] */
+struct acc4_t {
+    unsigned long long p01, p23;
+    __device__ __forceinline__ void zero() { p01 = 0ull; p23 = 0ull; }
+    __device__ __forceinline__ void to(float (&v)[4]) const { unpack2f(p01, v[0], v[1]); unpack2f(p23, v[2], v[3]); }
+};
+
 /* ---- f32 -------------------------------------------------------------------------------- */
 
 __device__ __forceinline__ float reduce16_f32(float const v[4]) {
@@ -81,17 +114,19 @@ struct l2sq_f32_t {
     static constexpr bool NORMS = false;
     template <class Q> static __device__ __forceinline__ float finalize(float raw, Q, float) { return raw; }
     template <class Q> static __device__ __forceinline__ float finalize_sw(float raw, Q, float) { return raw; }
-    struct acc_t { float v[4]; };
+    using acc_t = acc4_t;
     struct qconst_t {};
-    static __device__ __forceinline__ void init(acc_t& a) { a.v[0] = a.v[1] = a.v[2] = a.v[3] = 0.f; }
+    static __device__ __forceinline__ void init(acc_t& a) { a.zero(); }
     static __device__ __forceinline__ void step(acc_t& a, uint4 b, uint4 q) {
-        float x;
-        x = __fsub_rn(__uint_as_float(q.x), __uint_as_float(b.x)); a.v[0] = __fmaf_rn(x, x, a.v[0]);
-        x = __fsub_rn(__uint_as_float(q.y), __uint_as_float(b.y)); a.v[1] = __fmaf_rn(x, x, a.v[1]);
-        x = __fsub_rn(__uint_as_float(q.z), __uint_as_float(b.z)); a.v[2] = __fmaf_rn(x, x, a.v[2]);
-        x = __fsub_rn(__uint_as_float(q.w), __uint_as_float(b.w)); a.v[3] = __fmaf_rn(x, x, a.v[3]);
+        unsigned long long const x01 = sub2(pack2(q.x, q.y), pack2(b.x, b.y)), x23 = sub2(pack2(q.z, q.w), pack2(b.z, b.w));
+        fma2(a.p01, x01, x01);
+        fma2(a.p23, x23, x23);
     }
-    static __device__ __forceinline__ float finish(acc_t const& a, qconst_t) { return reduce16_f32(a.v); }
+    static __device__ __forceinline__ float finish(acc_t const& a, qconst_t) {
+        float v[4];
+        a.to(v);
+        return reduce16_f32(v);
+    }
     static __device__ __forceinline__ qconst_t prepare(uint4 const*, uint32_t, int) { return {}; }
 };
 
@@ -100,17 +135,17 @@ struct ip_f32_t {
     static constexpr bool NORMS = false;
     template <class Q> static __device__ __forceinline__ float finalize(float raw, Q, float) { return raw; }
     template <class Q> static __device__ __forceinline__ float finalize_sw(float raw, Q, float) { return raw; }
-    struct acc_t { float v[4]; };
+    using acc_t = acc4_t;
     struct qconst_t {};
-    static __device__ __forceinline__ void init(acc_t& a) { a.v[0] = a.v[1] = a.v[2] = a.v[3] = 0.f; }
+    static __device__ __forceinline__ void init(acc_t& a) { a.zero(); }
     static __device__ __forceinline__ void step(acc_t& a, uint4 b, uint4 q) {
-        a.v[0] = __fmaf_rn(__uint_as_float(q.x), __uint_as_float(b.x), a.v[0]);
-        a.v[1] = __fmaf_rn(__uint_as_float(q.y), __uint_as_float(b.y), a.v[1]);
-        a.v[2] = __fmaf_rn(__uint_as_float(q.z), __uint_as_float(b.z), a.v[2]);
-        a.v[3] = __fmaf_rn(__uint_as_float(q.w), __uint_as_float(b.w), a.v[3]);
+        fma2(a.p01, pack2(q.x, q.y), pack2(b.x, b.y));
+        fma2(a.p23, pack2(q.z, q.w), pack2(b.z, b.w));
     }
     static __device__ __forceinline__ float finish(acc_t const& a, qconst_t) {
-        return __fsub_rn(1.0f, reduce16_f32(a.v));
+        float v[4];
+        a.to(v);
+        return __fsub_rn(1.0f, reduce16_f32(v));
     }
     static __device__ __forceinline__ qconst_t prepare(uint4 const*, uint32_t, int) { return {}; }
 };
@@ -123,16 +158,18 @@ struct ip_f32_t {
 struct cos_f32_t {
     static constexpr int LPV = 4;
     static constexpr bool NORMS = true;
-    struct acc_t { float ab[4]; };
+    using acc_t = acc4_t;
     struct qconst_t { float a2; };
-    static __device__ __forceinline__ void init(acc_t& a) { a.ab[0] = a.ab[1] = a.ab[2] = a.ab[3] = 0.f; }
+    static __device__ __forceinline__ void init(acc_t& a) { a.zero(); }
     static __device__ __forceinline__ void step(acc_t& a, uint4 b, uint4 q) {
-        a.ab[0] = __fmaf_rn(__uint_as_float(q.x), __uint_as_float(b.x), a.ab[0]);
-        a.ab[1] = __fmaf_rn(__uint_as_float(q.y), __uint_as_float(b.y), a.ab[1]);
-        a.ab[2] = __fmaf_rn(__uint_as_float(q.z), __uint_as_float(b.z), a.ab[2]);
-        a.ab[3] = __fmaf_rn(__uint_as_float(q.w), __uint_as_float(b.w), a.ab[3]);
+        fma2(a.p01, pack2(q.x, q.y), pack2(b.x, b.y));
+        fma2(a.p23, pack2(q.z, q.w), pack2(b.z, b.w));
     }
-    static __device__ __forceinline__ float finish(acc_t const& a, qconst_t) { return reduce16_f32(a.ab); }
+    static __device__ __forceinline__ float finish(acc_t const& a, qconst_t) {
+        float v[4];
+        a.to(v);
+        return reduce16_f32(v);
+    }
     static __device__ __forceinline__ float finalize(float ab, qconst_t qc, float b2) { return cos_normalize_f64(ab, qc.a2, b2); }
     /* metric(stored, query) instead of metric(query, stored): exact_search_t calls it that way (index_plugins.hpp:2112) */
     static __device__ __forceinline__ float finalize_sw(float ab, qconst_t qc, float b2) { return cos_normalize_f64(ab, b2, qc.a2); }
@@ -319,18 +356,21 @@ template <class C> struct l2sq_halfw_t {
     static constexpr bool NORMS = false;
     using unit_t = uint32_t;
     template <class Q> static __device__ __forceinline__ float finalize(float raw, Q, float) { return raw; }
-    struct acc_t { float v[2]; };
+    struct acc_t { unsigned long long p; };
     struct qconst_t {};
-    static __device__ __forceinline__ void init(acc_t& a) { a.v[0] = a.v[1] = 0.f; }
+    static __device__ __forceinline__ void init(acc_t& a) { a.p = 0ull; }
     static __device__ __forceinline__ void step(acc_t& a, uint32_t b, uint32_t q) {
         float b0, b1, q0, q1;
         C::widen(b, b0, b1);
         C::widen(q, q0, q1);
-        float x0 = __fsub_rn(q0, b0), x1 = __fsub_rn(q1, b1);
-        a.v[0] = __fmaf_rn(x0, x0, a.v[0]);
-        a.v[1] = __fmaf_rn(x1, x1, a.v[1]);
+        unsigned long long const x = sub2(pack2f(q0, q1), pack2f(b0, b1));
+        fma2(a.p, x, x);
     }
-    static __device__ __forceinline__ float finish(acc_t const& a, qconst_t) { return reduce_words_f64(a.v); }
+    static __device__ __forceinline__ float finish(acc_t const& a, qconst_t) {
+        float v[2];
+        unpack2f(a.p, v[0], v[1]);
+        return reduce_words_f64(v);
+    }
     static __device__ __forceinline__ qconst_t prepare(uint4 const*, uint32_t, int) { return {}; }
 };
 
@@ -339,17 +379,20 @@ template <class C> struct ip_halfw_t {
     static constexpr bool NORMS = false;
     using unit_t = uint32_t;
     template <class Q> static __device__ __forceinline__ float finalize(float raw, Q, float) { return raw; }
-    struct acc_t { float v[2]; };
+    struct acc_t { unsigned long long p; };
     struct qconst_t {};
-    static __device__ __forceinline__ void init(acc_t& a) { a.v[0] = a.v[1] = 0.f; }
+    static __device__ __forceinline__ void init(acc_t& a) { a.p = 0ull; }
     static __device__ __forceinline__ void step(acc_t& a, uint32_t b, uint32_t q) {
         float b0, b1, q0, q1;
         C::widen(b, b0, b1);
         C::widen(q, q0, q1);
-        a.v[0] = __fmaf_rn(q0, b0, a.v[0]);
-        a.v[1] = __fmaf_rn(q1, b1, a.v[1]);
+        fma2(a.p, pack2f(q0, q1), pack2f(b0, b1));
     }
-    static __device__ __forceinline__ float finish(acc_t const& a, qconst_t) { return __fsub_rn(1.0f, reduce_words_f64(a.v)); }
+    static __device__ __forceinline__ float finish(acc_t const& a, qconst_t) {
+        float v[2];
+        unpack2f(a.p, v[0], v[1]);
+        return __fsub_rn(1.0f, reduce_words_f64(v));
+    }
     static __device__ __forceinline__ qconst_t prepare(uint4 const*, uint32_t, int) { return {}; }
 };
 
@@ -357,17 +400,20 @@ template <class C> struct cos_halfw_t {
     static constexpr int LPV = 4, UPC = 4;
     static constexpr bool NORMS = true;
     using unit_t = uint32_t;
-    struct acc_t { float v[2]; };
+    struct acc_t { unsigned long long p; };
     using qconst_t = typename cos_half_t<C>::qconst_t;
-    static __device__ __forceinline__ void init(acc_t& a) { a.v[0] = a.v[1] = 0.f; }
+    static __device__ __forceinline__ void init(acc_t& a) { a.p = 0ull; }
     static __device__ __forceinline__ void step(acc_t& a, uint32_t b, uint32_t q) {
         float b0, b1, q0, q1;
         C::widen(b, b0, b1);
         C::widen(q, q0, q1);
-        a.v[0] = __fmaf_rn(q0, b0, a.v[0]);
-        a.v[1] = __fmaf_rn(q1, b1, a.v[1]);
+        fma2(a.p, pack2f(q0, q1), pack2f(b0, b1));
     }
-    static __device__ __forceinline__ float finish(acc_t const& a, qconst_t) { return reduce_words_f64(a.v); }
+    static __device__ __forceinline__ float finish(acc_t const& a, qconst_t) {
+        float v[2];
+        unpack2f(a.p, v[0], v[1]);
+        return reduce_words_f64(v);
+    }
     static __device__ __forceinline__ float finalize(float ab, qconst_t qc, float b2) { return cos_normalize_f32(ab, qc.a2, b2); }
     static __device__ __forceinline__ qconst_t prepare(uint4 const* q4, uint32_t chunks16, int lane) {
         return cos_half_t<C>::prepare(q4, chunks16, lane); /* the query's own norm: same chain as the stored norms */

@@ -360,8 +360,32 @@ __device__ __forceinline__ void measure_staged(device_index_t const& ix, search_
             }
         }
     };
-    issue(0);
-    if (nsets > 1 && nsp > 1) issue(1);
+    /* The same segment pass requested with 16-byte cp.async (LDGSTS) instead: lane l copies bytes 16*l + 512*i of every
+     * vector of the pass, so a 3 KB vector is six fully coalesced warp instructions with immediate offsets and nothing is
+     * serialised. Completion is per-thread group accounting (commit_group / wait_group) plus a warp barrier; no mbarrier. */
+    auto issue_ldgsts = [&](uint32_t sp) {
+        uint32_t const pass = sp / segs, h = sp - pass * segs;
+        uint32_t const base = pass * VPP, cnt = min((uint32_t)VPP, ncand - base), set = sp % nsets;
+        uint32_t const c0 = h * seg_chunks, nch = min(chunks, c0 + seg_chunks) - c0;
+        for (uint32_t i = 0; i < cnt; ++i) {
+            uint32_t const slot = w.cand_s[base + i];
+            uint8_t const* src = ix.vectors + (size_t)slot * ix.vec_stride + (size_t)c0 * 16u + (size_t)lane * 16u;
+            uint32_t const dst = w.stage_addr + (set * VPP + i) * a.stage_stride + (uint32_t)lane * 16u;
+            for (uint32_t j = lane; j < nch; j += 32) {
+                uint32_t const off = (j - (uint32_t)lane) * 16u; /* 0, 512, 1024, ... */
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + off), "l"(src + off) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    bool const ldgsts = a.stage_copy != 0;
+    if (ldgsts) {
+        issue_ldgsts(0);
+        if (nsets > 1 && nsp > 1) issue_ldgsts(1);
+    } else {
+        issue(0);
+        if (nsets > 1 && nsp > 1) issue(1);
+    }
     typename M::acc_t acc;
     M::init(acc);
     for (uint32_t sp = 0; sp < nsp; ++sp) {
@@ -377,14 +401,20 @@ __device__ __forceinline__ void measure_staged(device_index_t const& ix, search_
         U const* qu = reinterpret_cast<U const*>(w.q4);
         bool const act = (uint32_t)g < cnt;
         if (h == 0) M::init(acc);
-        if (a.phase_cycles) { /* introspection only: attribute the wait for the slowest slot to `vector_wait` */
+        if (ldgsts) { /* groups complete in order: all but the pass requested after this one must have landed */
+            long long const t = a.phase_cycles ? clock64() : 0;
+            if (nsets > 1 && sp + 1 < nsp) asm volatile("cp.async.wait_group 1;" ::: "memory");
+            else asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+            if (a.phase_cycles) w.t_wait += (uint32_t)(clock64() - t);
+        } else if (a.phase_cycles) { /* introspection only: attribute the wait for the slowest slot to `vector_wait` */
             long long t = clock64();
             if (act) mbar_wait(w.bars_addr + 8u * set, (w.phase >> set) & 1u);
             __syncwarp();
             w.t_wait += (uint32_t)(clock64() - t);
         }
         if (act) {
-            if (!a.phase_cycles) mbar_wait(w.bars_addr + 8u * set, (w.phase >> set) & 1u);
+            if (!a.phase_cycles && !ldgsts) mbar_wait(w.bars_addr + 8u * set, (w.phase >> set) & 1u);
             /* 4 steps per iteration, the next iteration's 8 shared-memory loads issued before this one's math */
             uint32_t j = u0 + sub;
             if (j + 3 * LPV < u1) {
@@ -412,9 +442,12 @@ __device__ __forceinline__ void measure_staged(device_index_t const& ix, search_
             float d = M::finish(acc, qc);
             if (act && sub == 0) w.cand_d[base + g] = d;
         }
-        w.phase ^= 1u << set; /* one parity bit per set */
-        __syncwarp();         /* every lane is done with this set before it is refilled */
-        if (sp + nsets < nsp) issue(sp + nsets);
+        if (!ldgsts) w.phase ^= 1u << set; /* one parity bit per set */
+        __syncwarp();                      /* every lane is done with this set before it is refilled */
+        if (sp + nsets < nsp) {
+            if (ldgsts) issue_ldgsts(sp + nsets);
+            else issue(sp + nsets);
+        }
     }
 }
 
@@ -727,19 +760,6 @@ __device__ __forceinline__ void search_one(device_index_t const& ix, search_args
 
             measure_list<M, STAGED>(ix, a, w, qc, ncand, lane);
             computed += ncand;
-            /* Speculation, one step further than the row prefetch: the accept replay below, the pop and the visited
-             * round trip of the next hop keep this warp off the memory system for a microsecond or two. Unless this
-             * hop found something closer, `pre_node` is expanded next: ask L2 for those of its neighbours whose bit
-             * is still clear (a plain read of the bitmap word; nothing is marked). A wrong guess costs bandwidth, never
-             * correctness. */
-            if (a.prefetch_next && bitmap && pre_node != EMPTY_SLOT) {
-                uint32_t const w0 = pre_s0 != EMPTY_SLOT ? ld_l2_u32(&visited[pre_s0 >> 5]) : 0xFFFFFFFFu;
-                uint32_t const w1 = pre_s1 != EMPTY_SLOT ? ld_l2_u32(&visited[pre_s1 >> 5]) : 0xFFFFFFFFu;
-                if (pre_s0 != EMPTY_SLOT && !((w0 >> (pre_s0 & 31)) & 1u))
-                    bulk_prefetch_l2(ix.vectors + (size_t)pre_s0 * ix.vec_stride, (uint32_t)ix.vec_stride);
-                if (pre_s1 != EMPTY_SLOT && !((w1 >> (pre_s1 & 31)) & 1u))
-                    bulk_prefetch_l2(ix.vectors + (size_t)pre_s1 * ix.vec_stride, (uint32_t)ix.vec_stride);
-            }
             PHASE(pc4)
 
             /* The reference's sequential accept loop, replayed in stored order. `radius` only shrinks
@@ -784,8 +804,20 @@ __device__ __forceinline__ void search_one(device_index_t const& ix, search_args
     if (ix.n != 0 && k != 0 && a.visited_bitmap_words != 0 && a.visit_log != nullptr) {
         __syncwarp();
         if (!log_overflow_out) {
+            /* eight independent log reads in flight per lane: the loop is a chain of L2 round trips otherwise
+             * (measured at 10M x 768: 6 % of the kernel in this loop before the unrolling) */
             uint32_t const* vlog = a.visit_log + (size_t)blockIdx.x * a.visit_log_cap;
-            for (uint32_t i = lane; i < visited_total; i += 32) visited[vlog[i] >> 5] = 0u;
+            for (uint32_t i0 = 0; i0 < visited_total; i0 += 32 * 8) {
+                uint32_t e[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    uint32_t const i = i0 + (uint32_t)(u * 32 + lane);
+                    e[u] = i < visited_total ? vlog[i] : EMPTY_SLOT;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (e[u] != EMPTY_SLOT) visited[e[u] >> 5] = 0u;
+            }
         } else {
             uint4 const zero = make_uint4(0u, 0u, 0u, 0u);
             uint4* v4 = reinterpret_cast<uint4*>(visited);
@@ -1024,10 +1056,11 @@ template <class M, bool STAGED, int MIN_CTAS> static cudaError_t occupancy_k(int
         if (ix.metric == METRIC_IP) return staged ? OP<ip_i8_t<4>, true, 16> ARGS : OP<ip_i8_t<4>, false, 16> ARGS; \
         if (ix.metric == METRIC_COS) return staged ? OP<cos_i8_t<4>, true, 16> ARGS : OP<cos_i8_t<4>, false, 16> ARGS; \
         break;                                                                                                  \
-    case SCALAR_B1:                                                                                             \
-        if (ix.metric == METRIC_HAMMING) return OP<hamming_b1_t<2>, false, 16> ARGS;                            \
-        if (ix.metric == METRIC_TANIMOTO || ix.metric == METRIC_JACCARD) return OP<tanimoto_b1_t<2>, false, 16> ARGS; \
-        if (ix.metric == METRIC_SORENSEN) return OP<sorensen_b1_t<2>, false, 16> ARGS;                          \
+    case SCALAR_B1: /* `dense`: compiled for 24 resident warps per SM (<= 85 registers) instead of 16 */      \
+        if (ix.metric == METRIC_HAMMING) return dense ? OP<hamming_b1_t<2>, false, 24> ARGS : OP<hamming_b1_t<2>, false, 16> ARGS; \
+        if (ix.metric == METRIC_TANIMOTO || ix.metric == METRIC_JACCARD)                                       \
+            return dense ? OP<tanimoto_b1_t<2>, false, 24> ARGS : OP<tanimoto_b1_t<2>, false, 16> ARGS;         \
+        if (ix.metric == METRIC_SORENSEN) return dense ? OP<sorensen_b1_t<2>, false, 24> ARGS : OP<sorensen_b1_t<2>, false, 16> ARGS; \
         break;                                                                                                  \
     default: break;                                                                                             \
     }                                                                                                           \
@@ -1054,11 +1087,11 @@ bool search_single_stage_set(device_index_t const& ix) {
 }
 
 cudaError_t search_launch(device_index_t const& ix, search_args_t const& a, int blocks, size_t smem, cudaStream_t stream) {
-    bool const staged = search_is_staged(ix);
+    bool const staged = search_is_staged(ix), dense = a.dense_direct != 0;
     FOR_METRIC(launch_k, (ix, a, blocks, smem, stream))
 }
 
-cudaError_t search_occupancy(device_index_t const& ix, int* blocks_per_sm, size_t smem) {
+cudaError_t search_occupancy(device_index_t const& ix, bool dense, int* blocks_per_sm, size_t smem) {
     bool const staged = search_is_staged(ix);
     FOR_METRIC(occupancy_k, (blocks_per_sm, smem))
 }
