@@ -224,6 +224,60 @@ class index_dense_t {
         return result;
     }
 
+    /* ---- mutation and lookups by key: add_result_t / labeling_result_t of the reference, trimmed (index.hpp:2548-2562,
+     *      index_dense.hpp:525-540) ---- */
+    struct add_result_t {
+        error_t error{};
+        std::size_t new_size = 0;
+        explicit operator bool() const noexcept { return !error; }
+    };
+    struct labeling_result_t {
+        error_t error{};
+        std::size_t completed = 0;
+        explicit operator bool() const noexcept { return !error; }
+    };
+    error_t reserve(std::size_t capacity) { usearch_error_t e = nullptr; usearch_reserve(handle_, capacity, &e); return e; }
+    bool try_reserve(std::size_t capacity) { return !reserve(capacity); }
+    /* index_dense.hpp:760-765 — `thread` and `copy_vector` are accepted and ignored (the index always owns a copy in HBM) */
+    template <typename scalar_at> add_result_t add(vector_key_t key, scalar_at const* vector, std::size_t /*thread*/ = 0, bool /*copy*/ = true) {
+        add_result_t result;
+        usearch_error_t error = nullptr;
+        usearch_add(handle_, key, vector, scalar_kind<scalar_at>(), &error);
+        result.error = error;
+        result.new_size = size();
+        return result;
+    }
+    /* the batch driver of python/lib.cpp:171-258 as one call: the graph is linked on the GPU */
+    template <typename scalar_at>
+    add_result_t add_many(vector_key_t const* keys, scalar_at const* vectors, std::size_t count, std::size_t stride_bytes = 0) {
+        add_result_t result;
+        usearch_error_t error = nullptr;
+        usearch_b200_add_many(handle_, keys, vectors, count, stride_bytes, scalar_kind<scalar_at>(), &error);
+        result.error = error;
+        result.new_size = size();
+        return result;
+    }
+    bool contains(vector_key_t key) const { return usearch_contains(handle_, key, nullptr); }
+    std::size_t count(vector_key_t key) const { return usearch_count(handle_, key, nullptr); }
+    template <typename scalar_at> std::size_t get(vector_key_t key, scalar_at* vectors, std::size_t vectors_limit = 1) const {
+        usearch_error_t error = nullptr;
+        return usearch_get(handle_, key, vectors_limit, vectors, scalar_kind<scalar_at>(), &error);
+    }
+    labeling_result_t remove(vector_key_t key) {
+        labeling_result_t result;
+        usearch_error_t error = nullptr;
+        result.completed = usearch_remove(handle_, key, &error);
+        result.error = error;
+        return result;
+    }
+    labeling_result_t rename(vector_key_t from, vector_key_t to) {
+        labeling_result_t result;
+        usearch_error_t error = nullptr;
+        result.completed = usearch_rename(handle_, from, to, &error);
+        result.error = error;
+        return result;
+    }
+
     /* cluster_result_t (index.hpp:2744-2755) and index_dense_gt::cluster(vector, level) (index_dense.hpp:788-793) */
     struct cluster_result_t {
         error_t error{};

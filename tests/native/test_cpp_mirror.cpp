@@ -90,6 +90,28 @@ int main(int argc, char** argv) {
     index_dense_t::state_result_t bad = index_dense_t::make(metric_punned_t::builtin(dims, usearch_metric_haversine_k, usearch_scalar_f32_k));
     EXPECT(!bad);
 
+    // the mutation half of index_dense_gt on an index made from a metric: reserve / add / add_many / contains / count / get /
+    // rename / remove, then the new members are found by the search (cpp/test.cpp:358-361: a member is its own nearest)
+    {
+        index_dense_t& built = fresh.index;
+        EXPECT(built.try_reserve(nq + 4));
+        EXPECT(built.add(1000, queries.data()) && built.size() == 1);
+        std::vector<vector_key_t> keys2;
+        for (unsigned long long q = 1; q != nq; ++q) keys2.push_back(1000 + q);
+        index_dense_t::add_result_t added = built.add_many(keys2.data(), queries.data() + dims, nq - 1);
+        EXPECT(added && added.new_size == nq && built.size() == nq);
+        EXPECT(!built.add(1000, queries.data()));                       // duplicate key on a non-multi index
+        EXPECT(built.contains(1003) && built.count(1003) == 1 && !built.contains(7));
+        std::vector<float> stored(dims);
+        EXPECT(built.get(1003, stored.data()) == 1 && std::memcmp(stored.data(), queries.data() + 3 * dims, dims * 4) == 0);
+        index_dense_t::search_result_t self = built.search(queries.data() + 5 * dims, 3);
+        EXPECT(self && self.size() >= 1 && self[0].member.key == 1005 && self[0].distance < 1e-5f);
+        EXPECT(built.rename(1005, 2005).completed == 1 && built.contains(2005) && !built.contains(1005));
+        EXPECT(built.remove(2005).completed == 1 && built.size() == nq - 1);
+        self = built.search(queries.data() + 5 * dims, 3);
+        for (std::size_t i = 0; i != self.size(); ++i) EXPECT(self[i].member.key != 2005);
+    }
+
     std::printf("CPP_MIRROR_OK %llu queries\n", nq);
     return 0;
 }

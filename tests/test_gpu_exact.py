@@ -149,3 +149,35 @@ def test_cluster_matches_reference(metric, scalar, n, d, m):
     got = index.search(q, 10, stats=True)
     common.assert_same_results(want, (got.keys, got.distances, got.counts, index.last_computed, index.last_visited), "after cluster")
 
+
+
+@pytest.mark.parametrize("kernel", ["imma", "umma", "tiled"])
+def test_i8_exact_kernels_agree_with_the_reference(kernel):
+    """The three i8 scans — tcgen05 with TMEM accumulators (default), mma.sync, dp4a — forced one at a time
+    (USEARCH_B200_EXACT is read once per process, hence the subprocess): same bits, index mode and free function."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import numpy as np, common\n"
+        "from oracle import bindings\n"
+        "from usearch_b200.index import Index, exact_search\n"
+        "for metric, n, d, k, nq, removed in (('ip', 5000, 1024, 10, 150, 0), ('l2sq', 7000, 200, 33, 300, 40), ('cos', 3000, 768, 100, 70, 10), ('ip', 700, 96, 256, 9, 0)):\n"
+        "    base, q = common.make_collection(n, d, 'i8', nq)\n"
+        "    base[n // 2:n // 2 + 30] = base[:30]\n"
+        "    keys = np.arange(n, dtype=np.uint64) * 5 + 1\n"
+        "    ref, _ = common.build_reference_blob(base, metric, 'i8', d, 8, expansion_add=16, threads=16, keys=keys)\n"
+        "    for key in keys[3:3 + removed]: ref.remove(int(key))\n"
+        "    blob = ref.save(); ref.pin_metric(True)\n"
+        "    want = ref.search(q, k, threads=8, exact=True)\n"
+        "    got = Index.restore(blob).search(q, k, exact=True)\n"
+        "    common.assert_same_results(want[:3], (got.keys, got.distances, got.counts), metric)\n"
+        "    wk, wd = bindings.ref_exact_search(base, q, k, metric=metric, scalar='i8', dims=d)\n"
+        "    free = exact_search(base, q, k, metric=metric, dtype='i8')\n"
+        "    assert np.array_equal(free.distances.view(np.uint32), wd.view(np.uint32)), metric\n"
+        "print('I8_EXACT_OK')\n"
+    ) % (common.ROOT, os.path.join(common.ROOT, "tests"))
+    env = dict(os.environ, USEARCH_B200_EXACT=kernel)
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "I8_EXACT_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]

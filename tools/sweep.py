@@ -1,6 +1,6 @@
 """Build one bench workload on the GPU, then time the search kernel under several launch configurations in ONE process.
 
-    python tools/sweep.py --workload NS --configs "base;stage_copy=1;stage_copy=1,warps_per_sm=3" --steps 6
+    python tools/sweep.py --workload NS --configs "base;warps_per_sm=3;stage_sets=1" --steps 6
 
 Prints one JSON line per configuration: kernel ms per launch (CUDA events inside the library), algorithmic GB/s and the
 fraction of the measured HBM peak (the roofline figure of bench.py), recall on the first batch."""
@@ -26,6 +26,7 @@ def main():
     p.add_argument("--configs", default="base")
     p.add_argument("--steps", type=int, default=6)
     p.add_argument("--phases", action="store_true", help="also print the kernel's per-phase cycle counters")
+    p.add_argument("--ncu", action="store_true", help="cudaProfilerStart/Stop around the LAST step of every configuration (ncu --profile-from-start off)")
     o = p.parse_args()
     import torch
     sys.argv = ["bench.py", "--workload", o.workload] + (["--n", str(o.n)] if o.n else []) + (["--batch", str(o.batch)] if o.batch else []) + \
@@ -59,7 +60,7 @@ def main():
     m0 = 2 * index.connectivity
     print(json.dumps({"workload": bench.workload_name(a), "build_s": round(build_s, 1), "hbm_gb": round(index.memory_usage / 1e9, 2)}), flush=True)
     for spec in o.configs.split(";"):
-        knobs = {"stage_sets": 0, "warps_per_sm": 0, "issue_per_lane": 1, "stage_copy": 0, "dense_direct": 0}
+        knobs = {"stage_sets": 0, "warps_per_sm": 0, "issue_per_lane": 1}
         if spec != "base":
             for kv in spec.split(","):
                 name, value = kv.split("=")
@@ -71,8 +72,13 @@ def main():
             index.profile_phases(True)
         for s in range(o.steps + 2):
             qs = q_bytes[s * B:(s + 1) * B]
+            if o.ncu and s == o.steps + 1:
+                torch.cuda.profiler.start()
             index.search_device(qs.data_ptr(), B, vs, k, keys.data_ptr(), dist.data_ptr(), cnt.data_ptr(), comp.data_ptr(), vis.data_ptr(),
                                 stream.cuda_stream)
+            if o.ncu and s == o.steps + 1:
+                torch.cuda.synchronize()
+                torch.cuda.profiler.stop()
             if s == 0:
                 rec = bench.recall_at_k(keys.cpu().numpy().astype(np.uint64)[:R], cnt.cpu().numpy()[:R], gt)
             if s >= 2:

@@ -111,10 +111,6 @@ struct search_args_t {
     uint32_t off_bars = 0, off_stage = 0, stage_stride = 0;
     uint32_t stage_segments = 1, stage_seg_chunks = 0; /* a vector is fetched as 1 or 2 copies of seg_chunks*16 bytes */
     uint32_t issue_per_lane = 0; /* tuning knob: 1 = each lane issues its own bulk copy */
-    /* how staged vectors travel: 0 = one TMA bulk copy per vector (cp.async.bulk, mbarrier completion), 1 = 16-byte
-     * cp.async (LDGSTS) spread over the lanes, group completion */
-    uint32_t stage_copy = 0;
-    uint32_t dense_direct = 0; /* binary codes: the DIRECT kernel compiled for 24 instead of 16 resident warps per SM */
     uint32_t stage_sets = 1; /* 2 = double buffered: 2 x (32/LPV) slots, the next pass lands during the math */
     /* optional introspection: 8 cycle counters summed over all queries (lane 0 clock64 deltas):
      * setup+descent | heap pop | row + visited test | vector wait | distance math | accept replay | output */

@@ -35,4 +35,11 @@ int exact_imma_tile_vectors();
 cudaError_t exact_imma_self_dots(uint8_t const* rows, uint64_t stride, uint32_t chunks16, uint32_t count, int* out, cudaStream_t stream);
 cudaError_t exact_imma_launch(device_index_t const& ix, exact_args_t const& a, bool swap, dim3 grid, cudaStream_t stream);
 
+/* exact_umma.cu: the same scan on tcgen05 (TMEM accumulators, TMA operand loads) */
+size_t exact_umma_smem_bytes();
+int exact_umma_tile_queries();
+int exact_umma_tile_vectors();
+bool exact_umma_usable(device_index_t const& ix, exact_args_t const& a);
+cudaError_t exact_umma_launch(device_index_t const& ix, exact_args_t const& a, bool swap, dim3 grid, cudaStream_t stream);
+
 } // namespace usearch_b200

@@ -24,6 +24,7 @@
 
 #include "device_index.h"
 #include "exact_args.h"
+#include "exact_i8.cuh"
 #include "metrics.cuh"
 #include "warp_primitives.cuh"
 
@@ -49,24 +50,6 @@ __device__ __forceinline__ void imma_16832(int (&c)[4], uint32_t a0, uint32_t a1
                  : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
-
-/* cos: the two reciprocal roots of cos_normalize_f32 are per-operand (qr, vr), computed once per row / column of
- * the tile; the per-pair remainder is the same two multiplies and the subtraction, in the operand order of the
- * call (`metric(query, stored)` for an index, `metric(stored, query)` for exact_search_t) */
-template <uint32_t METRIC, bool SWAP>
-__device__ __forceinline__ float i8_distance(int ab, int qa2, int vb2, float qr, float vr) {
-    if constexpr (METRIC == METRIC_IP) return __fsub_rn(1.0f, __int2float_rn(ab));
-    else if constexpr (METRIC == METRIC_L2SQ) return __int2float_rn(qa2 + vb2 - 2 * ab);
-    else {
-        if (qa2 == 0 && vb2 == 0) return 0.0f;
-        if (ab == 0) return 1.0f;
-        float const abf = __int2float_rn(ab);
-        float const r = SWAP ? __fsub_rn(1.0f, __fmul_rn(__fmul_rn(abf, vr), qr)) : __fsub_rn(1.0f, __fmul_rn(__fmul_rn(abf, qr), vr));
-        return r > 0 ? r : 0.f;
-    }
-}
-
-__device__ __forceinline__ float i8_rnorm(int x2) { return __frcp_rn(__fsqrt_rn(__int2float_rn(x2))); }
 
 } // namespace
 

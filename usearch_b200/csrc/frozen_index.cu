@@ -512,7 +512,7 @@ char const* frozen_index_t::plan(uint32_t k, uint32_t visited_cap_override, laun
     }
 
     int per_sm = 0;
-    CU(search_occupancy(d, tune.dense_direct != 0, &per_sm, pl.smem_per_block));
+    CU(search_occupancy(d, &per_sm, pl.smem_per_block));
     if (per_sm < 1) return "Kernel does not fit on an SM";
     per_sm = std::min<int>(per_sm, (int)pl.warps_per_sm_target);
     pl.blocks = per_sm * sm_count;
@@ -559,8 +559,6 @@ char const* frozen_index_t::prepare_launch(launch_plan_t const& pl, size_t warps
     a.stage_seg_chunks = pl.stage_seg_chunks;
     /* measured on B200 (1M x 768 f32): per-lane issue 9.67 ms, single-lane back-to-back issue 10.33 ms */
     a.issue_per_lane = (uint32_t)tune.issue_per_lane;
-    a.stage_copy = (uint32_t)tune.stage_copy;
-    a.dense_direct = (uint32_t)tune.dense_direct;
     return nullptr;
 }
 

@@ -20,7 +20,7 @@ namespace usearch_b200 {
 
 /* kernel entry points (search_kernel.cu) */
 cudaError_t search_launch(device_index_t const& ix, search_args_t const& a, int blocks, size_t smem, cudaStream_t stream);
-cudaError_t search_occupancy(device_index_t const& ix, bool dense, int* blocks_per_sm, size_t smem);
+cudaError_t search_occupancy(device_index_t const& ix, int* blocks_per_sm, size_t smem);
 bool search_supported(uint32_t metric, uint32_t scalar);
 int search_warps_per_block();
 bool search_is_staged(device_index_t const& ix);
@@ -200,13 +200,11 @@ struct frozen_index_t {
     void* dev_allocs[8] = {nullptr};
 
     /* tuning knobs of the search launch: environment at construction (USEARCH_B200_STAGE_SETS, _WARPS_PER_SM,
-     * _ISSUE_PER_LANE, _STAGE_COPY), changeable per handle with usearch_b200_tune (bench sweeps, tests) */
+     * _ISSUE_PER_LANE), changeable per handle with usearch_b200_tune (bench sweeps, tests) */
     struct tune_t {
         int stage_sets = env_int("USEARCH_B200_STAGE_SETS", 0);     /* 0 = planned, 1 or 2 = forced */
         int warps_per_sm = env_int("USEARCH_B200_WARPS_PER_SM", 0); /* 0 = as many as fit, else an upper bound */
         int issue_per_lane = env_int("USEARCH_B200_ISSUE_PER_LANE", 1);
-        int stage_copy = env_int("USEARCH_B200_STAGE_COPY", 0);     /* 0 = TMA bulk copies, 1 = cp.async (LDGSTS) */
-        int dense_direct = env_int("USEARCH_B200_DENSE_DIRECT", 0); /* b1: 24-warp build of the DIRECT kernel */
         static int env_int(char const* name, int fallback) {
             char const* v = std::getenv(name);
             return v ? std::atoi(v) : fallback;

@@ -48,7 +48,11 @@ template <int LPV> __device__ __forceinline__ int reduce_add_i32(int v) {
 /*
  *  `fma.rn.f32x2` / `sub.rn.f32x2` (sm_100: SASS FFMA2 / FADD2) apply the scalar round-to-nearest operation to both halves
  *  of a 64-bit register pair. Every accumulator still sees the same operands in the same order, so the sums keep the bits
- *  of the scalar chains they replace (asserted by every parity test); the hot loops issue half as many FP instructions.
+ *  of the scalar chains they replace (asserted by every parity test). Used by the WORD half-precision metrics, where one
+ *  FFMA2 per 32-bit word replaces two scalar fmas (10M x 768 f16: 208 -> 191 ms per 65536 queries together with the log
+ *  cleaning). NOT used by the f32 metrics: there it turns four independent fma chains per lane into two, and with one warp
+ *  per scheduler the longer dependency distance costs more than the halved instruction count saves (measured at 10M x 768
+ *  f32: distance phase 1.60 M -> 1.96 M cycles per query).
  */
 __device__ __forceinline__ unsigned long long pack2(uint32_t lo, uint32_t hi) {
     unsigned long long r;
@@ -70,13 +74,6 @@ __device__ __forceinline__ unsigned long long sub2(unsigned long long a, unsigne
     asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
 }
-/* the four accumulators of a lane as two pairs <-> float[4] */
-struct acc4_t {
-    unsigned long long p01, p23;
-    __device__ __forceinline__ void zero() { p01 = 0ull; p23 = 0ull; }
-    __device__ __forceinline__ void to(float (&v)[4]) const { unpack2f(p01, v[0], v[1]); unpack2f(p23, v[2], v[3]); }
-};
-
 /* ---- f32 -------------------------------------------------------------------------------- */
 
 __device__ __forceinline__ float reduce16_f32(float const v[4]) {
@@ -114,19 +111,17 @@ struct l2sq_f32_t {
     static constexpr bool NORMS = false;
     template <class Q> static __device__ __forceinline__ float finalize(float raw, Q, float) { return raw; }
     template <class Q> static __device__ __forceinline__ float finalize_sw(float raw, Q, float) { return raw; }
-    using acc_t = acc4_t;
+    struct acc_t { float v[4]; };
     struct qconst_t {};
-    static __device__ __forceinline__ void init(acc_t& a) { a.zero(); }
+    static __device__ __forceinline__ void init(acc_t& a) { a.v[0] = a.v[1] = a.v[2] = a.v[3] = 0.f; }
     static __device__ __forceinline__ void step(acc_t& a, uint4 b, uint4 q) {
-        unsigned long long const x01 = sub2(pack2(q.x, q.y), pack2(b.x, b.y)), x23 = sub2(pack2(q.z, q.w), pack2(b.z, b.w));
-        fma2(a.p01, x01, x01);
-        fma2(a.p23, x23, x23);
+        float x;
+        x = __fsub_rn(__uint_as_float(q.x), __uint_as_float(b.x)); a.v[0] = __fmaf_rn(x, x, a.v[0]);
+        x = __fsub_rn(__uint_as_float(q.y), __uint_as_float(b.y)); a.v[1] = __fmaf_rn(x, x, a.v[1]);
+        x = __fsub_rn(__uint_as_float(q.z), __uint_as_float(b.z)); a.v[2] = __fmaf_rn(x, x, a.v[2]);
+        x = __fsub_rn(__uint_as_float(q.w), __uint_as_float(b.w)); a.v[3] = __fmaf_rn(x, x, a.v[3]);
     }
-    static __device__ __forceinline__ float finish(acc_t const& a, qconst_t) {
-        float v[4];
-        a.to(v);
-        return reduce16_f32(v);
-    }
+    static __device__ __forceinline__ float finish(acc_t const& a, qconst_t) { return reduce16_f32(a.v); }
     static __device__ __forceinline__ qconst_t prepare(uint4 const*, uint32_t, int) { return {}; }
 };
 
@@ -135,17 +130,17 @@ struct ip_f32_t {
     static constexpr bool NORMS = false;
     template <class Q> static __device__ __forceinline__ float finalize(float raw, Q, float) { return raw; }
     template <class Q> static __device__ __forceinline__ float finalize_sw(float raw, Q, float) { return raw; }
-    using acc_t = acc4_t;
+    struct acc_t { float v[4]; };
     struct qconst_t {};
-    static __device__ __forceinline__ void init(acc_t& a) { a.zero(); }
+    static __device__ __forceinline__ void init(acc_t& a) { a.v[0] = a.v[1] = a.v[2] = a.v[3] = 0.f; }
     static __device__ __forceinline__ void step(acc_t& a, uint4 b, uint4 q) {
-        fma2(a.p01, pack2(q.x, q.y), pack2(b.x, b.y));
-        fma2(a.p23, pack2(q.z, q.w), pack2(b.z, b.w));
+        a.v[0] = __fmaf_rn(__uint_as_float(q.x), __uint_as_float(b.x), a.v[0]);
+        a.v[1] = __fmaf_rn(__uint_as_float(q.y), __uint_as_float(b.y), a.v[1]);
+        a.v[2] = __fmaf_rn(__uint_as_float(q.z), __uint_as_float(b.z), a.v[2]);
+        a.v[3] = __fmaf_rn(__uint_as_float(q.w), __uint_as_float(b.w), a.v[3]);
     }
     static __device__ __forceinline__ float finish(acc_t const& a, qconst_t) {
-        float v[4];
-        a.to(v);
-        return __fsub_rn(1.0f, reduce16_f32(v));
+        return __fsub_rn(1.0f, reduce16_f32(a.v));
     }
     static __device__ __forceinline__ qconst_t prepare(uint4 const*, uint32_t, int) { return {}; }
 };
@@ -158,18 +153,16 @@ struct ip_f32_t {
 struct cos_f32_t {
     static constexpr int LPV = 4;
     static constexpr bool NORMS = true;
-    using acc_t = acc4_t;
+    struct acc_t { float ab[4]; };
     struct qconst_t { float a2; };
-    static __device__ __forceinline__ void init(acc_t& a) { a.zero(); }
+    static __device__ __forceinline__ void init(acc_t& a) { a.ab[0] = a.ab[1] = a.ab[2] = a.ab[3] = 0.f; }
     static __device__ __forceinline__ void step(acc_t& a, uint4 b, uint4 q) {
-        fma2(a.p01, pack2(q.x, q.y), pack2(b.x, b.y));
-        fma2(a.p23, pack2(q.z, q.w), pack2(b.z, b.w));
+        a.ab[0] = __fmaf_rn(__uint_as_float(q.x), __uint_as_float(b.x), a.ab[0]);
+        a.ab[1] = __fmaf_rn(__uint_as_float(q.y), __uint_as_float(b.y), a.ab[1]);
+        a.ab[2] = __fmaf_rn(__uint_as_float(q.z), __uint_as_float(b.z), a.ab[2]);
+        a.ab[3] = __fmaf_rn(__uint_as_float(q.w), __uint_as_float(b.w), a.ab[3]);
     }
-    static __device__ __forceinline__ float finish(acc_t const& a, qconst_t) {
-        float v[4];
-        a.to(v);
-        return reduce16_f32(v);
-    }
+    static __device__ __forceinline__ float finish(acc_t const& a, qconst_t) { return reduce16_f32(a.ab); }
     static __device__ __forceinline__ float finalize(float ab, qconst_t qc, float b2) { return cos_normalize_f64(ab, qc.a2, b2); }
     /* metric(stored, query) instead of metric(query, stored): exact_search_t calls it that way (index_plugins.hpp:2112) */
     static __device__ __forceinline__ float finalize_sw(float ab, qconst_t qc, float b2) { return cos_normalize_f64(ab, b2, qc.a2); }

@@ -360,32 +360,8 @@ __device__ __forceinline__ void measure_staged(device_index_t const& ix, search_
             }
         }
     };
-    /* The same segment pass requested with 16-byte cp.async (LDGSTS) instead: lane l copies bytes 16*l + 512*i of every
-     * vector of the pass, so a 3 KB vector is six fully coalesced warp instructions with immediate offsets and nothing is
-     * serialised. Completion is per-thread group accounting (commit_group / wait_group) plus a warp barrier; no mbarrier. */
-    auto issue_ldgsts = [&](uint32_t sp) {
-        uint32_t const pass = sp / segs, h = sp - pass * segs;
-        uint32_t const base = pass * VPP, cnt = min((uint32_t)VPP, ncand - base), set = sp % nsets;
-        uint32_t const c0 = h * seg_chunks, nch = min(chunks, c0 + seg_chunks) - c0;
-        for (uint32_t i = 0; i < cnt; ++i) {
-            uint32_t const slot = w.cand_s[base + i];
-            uint8_t const* src = ix.vectors + (size_t)slot * ix.vec_stride + (size_t)c0 * 16u + (size_t)lane * 16u;
-            uint32_t const dst = w.stage_addr + (set * VPP + i) * a.stage_stride + (uint32_t)lane * 16u;
-            for (uint32_t j = lane; j < nch; j += 32) {
-                uint32_t const off = (j - (uint32_t)lane) * 16u; /* 0, 512, 1024, ... */
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + off), "l"(src + off) : "memory");
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    bool const ldgsts = a.stage_copy != 0;
-    if (ldgsts) {
-        issue_ldgsts(0);
-        if (nsets > 1 && nsp > 1) issue_ldgsts(1);
-    } else {
-        issue(0);
-        if (nsets > 1 && nsp > 1) issue(1);
-    }
+    issue(0);
+    if (nsets > 1 && nsp > 1) issue(1);
     typename M::acc_t acc;
     M::init(acc);
     for (uint32_t sp = 0; sp < nsp; ++sp) {
@@ -401,20 +377,14 @@ __device__ __forceinline__ void measure_staged(device_index_t const& ix, search_
         U const* qu = reinterpret_cast<U const*>(w.q4);
         bool const act = (uint32_t)g < cnt;
         if (h == 0) M::init(acc);
-        if (ldgsts) { /* groups complete in order: all but the pass requested after this one must have landed */
-            long long const t = a.phase_cycles ? clock64() : 0;
-            if (nsets > 1 && sp + 1 < nsp) asm volatile("cp.async.wait_group 1;" ::: "memory");
-            else asm volatile("cp.async.wait_group 0;" ::: "memory");
-            __syncwarp();
-            if (a.phase_cycles) w.t_wait += (uint32_t)(clock64() - t);
-        } else if (a.phase_cycles) { /* introspection only: attribute the wait for the slowest slot to `vector_wait` */
+        if (a.phase_cycles) { /* introspection only: attribute the wait for the slowest slot to `vector_wait` */
             long long t = clock64();
             if (act) mbar_wait(w.bars_addr + 8u * set, (w.phase >> set) & 1u);
             __syncwarp();
             w.t_wait += (uint32_t)(clock64() - t);
         }
         if (act) {
-            if (!a.phase_cycles && !ldgsts) mbar_wait(w.bars_addr + 8u * set, (w.phase >> set) & 1u);
+            if (!a.phase_cycles) mbar_wait(w.bars_addr + 8u * set, (w.phase >> set) & 1u);
             /* 4 steps per iteration, the next iteration's 8 shared-memory loads issued before this one's math */
             uint32_t j = u0 + sub;
             if (j + 3 * LPV < u1) {
@@ -442,12 +412,9 @@ __device__ __forceinline__ void measure_staged(device_index_t const& ix, search_
             float d = M::finish(acc, qc);
             if (act && sub == 0) w.cand_d[base + g] = d;
         }
-        if (!ldgsts) w.phase ^= 1u << set; /* one parity bit per set */
-        __syncwarp();                      /* every lane is done with this set before it is refilled */
-        if (sp + nsets < nsp) {
-            if (ldgsts) issue_ldgsts(sp + nsets);
-            else issue(sp + nsets);
-        }
+        w.phase ^= 1u << set; /* one parity bit per set */
+        __syncwarp();         /* every lane is done with this set before it is refilled */
+        if (sp + nsets < nsp) issue(sp + nsets);
     }
 }
 
@@ -1056,11 +1023,10 @@ template <class M, bool STAGED, int MIN_CTAS> static cudaError_t occupancy_k(int
         if (ix.metric == METRIC_IP) return staged ? OP<ip_i8_t<4>, true, 16> ARGS : OP<ip_i8_t<4>, false, 16> ARGS; \
         if (ix.metric == METRIC_COS) return staged ? OP<cos_i8_t<4>, true, 16> ARGS : OP<cos_i8_t<4>, false, 16> ARGS; \
         break;                                                                                                  \
-    case SCALAR_B1: /* `dense`: compiled for 24 resident warps per SM (<= 85 registers) instead of 16 */      \
-        if (ix.metric == METRIC_HAMMING) return dense ? OP<hamming_b1_t<2>, false, 24> ARGS : OP<hamming_b1_t<2>, false, 16> ARGS; \
-        if (ix.metric == METRIC_TANIMOTO || ix.metric == METRIC_JACCARD)                                       \
-            return dense ? OP<tanimoto_b1_t<2>, false, 24> ARGS : OP<tanimoto_b1_t<2>, false, 16> ARGS;         \
-        if (ix.metric == METRIC_SORENSEN) return dense ? OP<sorensen_b1_t<2>, false, 24> ARGS : OP<sorensen_b1_t<2>, false, 16> ARGS; \
+    case SCALAR_B1:                                                                                             \
+        if (ix.metric == METRIC_HAMMING) return OP<hamming_b1_t<2>, false, 16> ARGS;                            \
+        if (ix.metric == METRIC_TANIMOTO || ix.metric == METRIC_JACCARD) return OP<tanimoto_b1_t<2>, false, 16> ARGS; \
+        if (ix.metric == METRIC_SORENSEN) return OP<sorensen_b1_t<2>, false, 16> ARGS;                          \
         break;                                                                                                  \
     default: break;                                                                                             \
     }                                                                                                           \
@@ -1087,11 +1053,11 @@ bool search_single_stage_set(device_index_t const& ix) {
 }
 
 cudaError_t search_launch(device_index_t const& ix, search_args_t const& a, int blocks, size_t smem, cudaStream_t stream) {
-    bool const staged = search_is_staged(ix), dense = a.dense_direct != 0;
+    bool const staged = search_is_staged(ix);
     FOR_METRIC(launch_k, (ix, a, blocks, smem, stream))
 }
 
-cudaError_t search_occupancy(device_index_t const& ix, bool dense, int* blocks_per_sm, size_t smem) {
+cudaError_t search_occupancy(device_index_t const& ix, int* blocks_per_sm, size_t smem) {
     bool const staged = search_is_staged(ix);
     FOR_METRIC(occupancy_k, (blocks_per_sm, smem))
 }

@@ -38,16 +38,6 @@ __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, void const* src, uin
                  : "memory");
 }
 
-/* whole-vector hint to L2 (cp.async.bulk.prefetch.L2): no destination, no completion to wait for */
-__device__ __forceinline__ void bulk_prefetch_l2(void const* src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_l2_u32(uint32_t const* p) {
-    uint32_t v;
-    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
-}
-
 /*
  *  Register-resident `top` for ef <= 256, BLOCKED layout: lane l holds elements 8l .. 8l+7. The same
  *  sorted_buffer_gt::insert semantics (index.hpp:928-939); the right-shift costs one shuffle per array:
