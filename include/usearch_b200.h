@@ -254,7 +254,7 @@ size_t usearch_b200_exact_search_many(usearch_index_t index, void const* queries
  * cycles of setup+descent | heap pop | row + visited test | vector wait | distance math | accept replay |
  * output, then queries | heap pushes | sum of per-query max heap size | max heap size | 5 reserved. */
 void usearch_b200_profile_phases(usearch_index_t index, int enable, uint64_t* counters16);
-/* Tuning knobs of the search launch for this handle ("stage_sets", "warps_per_sm", "issue_per_lane"); results
+/* Tuning knobs of the search launch for this handle ("stage_sets", "warps_per_sm"); results
  * never depend on them. Returns 0, or -1 for an unknown knob. */
 int usearch_b200_tune(usearch_index_t index, char const* knob, int value);
 int usearch_b200_device(usearch_index_t index);

@@ -60,7 +60,7 @@ def main():
     m0 = 2 * index.connectivity
     print(json.dumps({"workload": bench.workload_name(a), "build_s": round(build_s, 1), "hbm_gb": round(index.memory_usage / 1e9, 2)}), flush=True)
     for spec in o.configs.split(";"):
-        knobs = {"stage_sets": 0, "warps_per_sm": 0, "issue_per_lane": 1}
+        knobs = {"stage_sets": 0, "warps_per_sm": 0}
         if spec != "base":
             for kv in spec.split(","):
                 name, value = kv.split("=")

@@ -109,8 +109,6 @@ struct search_args_t {
     /* STAGED kernels: mbarriers and the slots TMA bulk copies land in (stride = 64 mod 128 bytes, so
      * that the 4-lane groups of a quarter-warp read disjoint banks) */
     uint32_t off_bars = 0, off_stage = 0, stage_stride = 0;
-    uint32_t stage_segments = 1, stage_seg_chunks = 0; /* a vector is fetched as 1 or 2 copies of seg_chunks*16 bytes */
-    uint32_t issue_per_lane = 0; /* tuning knob: 1 = each lane issues its own bulk copy */
     uint32_t stage_sets = 1; /* 2 = double buffered: 2 x (32/LPV) slots, the next pass lands during the math */
     /* optional introspection: 8 cycle counters summed over all queries (lane 0 clock64 deltas):
      * setup+descent | heap pop | row + visited test | vector wait | distance math | accept replay | output */

@@ -14,8 +14,11 @@
  *                    after the last k-block, hands the buffer to the epilogue
  *      warps 2..5    epilogue: thread = TMEM lane = query row. `tcgen05.ld` brings 32 columns at a time into registers; the
  *                    thread turns each integer dot product into the metric's float (i8_distance, shared with the IMMA
- *                    kernel), compares with the row's current worst and — rarely — inserts into that row's k-best list in
- *                    global memory under (distance ascending, slot descending). It overlaps with the MMAs of the next tile.
+ *                    kernel), compares with the row's current worst and — rarely — inserts into that row's k-best list
+ *                    under (distance ascending, slot descending). The lists live in SHARED memory (count <= 24; larger
+ *                    counts take the mma.sync kernel): with one thread per row an insertion is a chain of dependent loads
+ *                    that stalls the whole warp — in global memory (first version: 162 T multiply-adds/s, below the
+ *                    mma.sync kernel's 186) that chain cost more than the MMAs. It overlaps with the MMAs of the next tile.
  *  The per-(query, segment) lists are merged by exact_merge_kernel exactly as for the other scan kernels.
  */
 #include <cuda.h>
@@ -40,6 +43,10 @@ constexpr int UM_STAGES = 4;
 constexpr int UM_A_BYTES = UM_BM * UM_BK, UM_B_BYTES = UM_BN * UM_BK, UM_STAGE_BYTES = UM_A_BYTES + UM_B_BYTES; /* 48 KB */
 constexpr int UM_THREADS = 192; /* warps: 0 TMA, 1 MMA, 2..5 epilogue */
 constexpr int UM_TMEM_COLS = 512;
+constexpr int UM_KMAX = 24;        /* k-best lists of up to this many entries live in shared memory (row stride 25 words:
+                                      conflict-free when every lane touches the same position of its own row) */
+constexpr int UM_LIST_STRIDE = UM_KMAX + 1;
+constexpr int UM_LIST_BYTES = UM_BM * UM_LIST_STRIDE * 8;
 
 /* instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): dense, no saturate, D = s32 (2) at [4,6),
  * A = B = signed 8 bit (1) at [7,10) / [10,13), both K-major, N >> 3 at [17,23), M >> 4 at [24,29) */
@@ -91,7 +98,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, int (&v)[32]) {
 
 /* one thread, its own list: sorted insert under (distance ascending, slot descending), the order a sequence of
  * sorted_buffer_gt::insert calls in slot order converges to (search_exact_, index.hpp:4251-4268) */
-__device__ __forceinline__ void list_insert(float* ld, uint32_t* ls, uint32_t& size, uint32_t k, float cd, uint32_t cs) {
+__device__ __noinline__ void list_insert(float* ld, uint32_t* ls, uint32_t& size, uint32_t k, float cd, uint32_t cs) {
     uint32_t pos = size;
     while (pos > 0) { /* entries that sort after the candidate move one place to the right */
         float const d = ld[pos - 1];
@@ -193,8 +200,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1) exact_umma_kernel(__grid_consta
         int const qa2 = (METRIC != METRIC_IP && live) ? a.query_norms[qi] : 0;
         float const qr = METRIC == METRIC_COS ? i8_rnorm(qa2) : 0.f;
         size_t const list = live ? ((size_t)qi * a.segments + blockIdx.y) * a.k : 0;
-        float* const ld = a.part_d + list;
-        uint32_t* const ls = a.part_s + list;
+        float* const ld = reinterpret_cast<float*>(smem_raw + (stages - smem_u32(smem_raw)) + UM_STAGES * UM_STAGE_BYTES) + row * UM_LIST_STRIDE;
+        uint32_t* const ls = reinterpret_cast<uint32_t*>(ld - row * UM_LIST_STRIDE + UM_BM * UM_LIST_STRIDE) + row * UM_LIST_STRIDE;
         uint32_t size = 0;
         float worst = 0.f;
         for (uint32_t t = 0; t < ntiles; ++t) {
@@ -235,7 +242,10 @@ __global__ void __launch_bounds__(UM_THREADS, 1) exact_umma_kernel(__grid_consta
             if (lane == 0) mbar_arrive(tempty0 + 8u * buf);
             asm volatile("bar.sync 1, 128;" ::: "memory"); /* nobody overwrites col_* of this buffer before all have read it */
         }
-        if (live) a.part_n[(size_t)qi * a.segments + blockIdx.y] = size;
+        if (live) { /* the row's list -> the per-(query, segment) partial result */
+            for (uint32_t i = 0; i < size; ++i) { a.part_d[list + i] = ld[i]; a.part_s[list + i] = ls[i]; }
+            a.part_n[(size_t)qi * a.segments + blockIdx.y] = size;
+        }
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -293,13 +303,13 @@ cudaError_t umma_launch_t(device_index_t const& ix, exact_args_t const& a, bool 
 
 } // namespace
 
-size_t exact_umma_smem_bytes() { return (size_t)UM_STAGES * UM_STAGE_BYTES + 1024; }
+size_t exact_umma_smem_bytes() { return (size_t)UM_STAGES * UM_STAGE_BYTES + 1024 + UM_LIST_BYTES; }
 int exact_umma_tile_queries() { return UM_BM; }
 int exact_umma_tile_vectors() { return UM_BN; }
 
 /* false when the driver cannot encode tensor maps or the operands are not laid out for them: the caller falls back to IMMA */
 bool exact_umma_usable(device_index_t const& ix, exact_args_t const& a) {
-    return encode_tiled() != nullptr && (reinterpret_cast<uintptr_t>(ix.vectors) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.queries) & 15) == 0 &&
+    return a.k <= (uint32_t)UM_KMAX && encode_tiled() != nullptr && (reinterpret_cast<uintptr_t>(ix.vectors) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.queries) & 15) == 0 &&
            (a.query_stride & 15) == 0 && (ix.vec_stride & 15) == 0;
 }
 

@@ -430,36 +430,21 @@ char const* frozen_index_t::plan(uint32_t k, uint32_t visited_cap_override, laun
     off = round_up(off, 128);
     pl.off_stage = off;
     int const slots = search_stage_slots(d); /* slots of one set: 32 / LPV */
-    uint32_t const lpv = (uint32_t)search_lanes_per_vector(d);
     /* an SM has 228 KB of shared memory and charges 1 KB per resident CTA on top of its request */
     size_t const smem_sm = 228 * 1024, cta_tax = 1024, smem_cta_max = 227 * 1024;
     uint32_t const min_heap = 128 * 8;
     int const forced_sets = tune.stage_sets;
-    static int const forced_segs = [] { char const* v = std::getenv("USEARCH_B200_STAGE_SEGMENTS"); return v ? std::atoi(v) : 0; }();
     pl.stage_sets = 1;
-    pl.stage_segments = 1;
-    pl.stage_seg_chunks = d.chunks16;
     pl.stage_stride = 0;
     if (slots) {
-        /* Long vectors CAN be fetched as two half-size segments (USEARCH_B200_STAGE_SEGMENTS=2): twice the copies
-         * for almost twice the resident warps (7 instead of 4 per SM at 768 x f32). Measured on B200 it is a wash
-         * (9.90 ms vs 9.79 ms per 4096-query batch): the kernel is limited by shared-memory traffic per vector,
-         * not by thread-level parallelism, so whole-vector slots stay the default. The split point is a multiple
-         * of 4*LPV chunks so that both halves run the unrolled loop. */
-        bool const can_split = lpv == 4 && search_stage_pad(d) == 64 && d.chunks16 >= 64;
-        uint32_t segs = 1u;
-        if (forced_segs == 2 && can_split) segs = 2u;
-        pl.stage_segments = segs;
-        pl.stage_seg_chunks = segs == 1 ? d.chunks16 : round_up((d.chunks16 + 1) / 2, 4 * lpv);
         /* slot stride = 16*LPV mod 128 bytes: the lanes of a quarter-warp then read disjoint banks */
-        pl.stage_stride = round_up(pl.stage_seg_chunks * 16, 128) + search_stage_pad(d);
+        pl.stage_stride = round_up(d.chunks16 * 16, 128) + search_stage_pad(d);
         /* double-buffer the slots when at least 4 warps per SM still fit */
         size_t const two = off + 2 * (size_t)slots * pl.stage_stride + min_heap + cta_tax;
         pl.stage_sets = smem_sm / two >= 4 ? 2u : 1u;
         /* short vectors of the 16-warp kernels: resident warps beat double buffering (search_kernel.cu, dispatch) */
         if (search_single_stage_set(d)) pl.stage_sets = 1;
         if (forced_sets == 1 || forced_sets == 2) pl.stage_sets = (uint32_t)forced_sets;
-        if (segs == 2) pl.stage_sets = 2; /* the two halves of a pass alternate between the two sets */
     }
     off += (uint32_t)slots * pl.stage_sets * pl.stage_stride;
     pl.off_heap = off;
@@ -555,10 +540,6 @@ char const* frozen_index_t::prepare_launch(launch_plan_t const& pl, size_t warps
     a.off_cand_d = pl.off_cand_d; a.off_heap = pl.off_heap;
     a.off_bars = pl.off_bars; a.off_stage = pl.off_stage; a.stage_stride = pl.stage_stride;
     a.stage_sets = pl.stage_sets;
-    a.stage_segments = pl.stage_segments;
-    a.stage_seg_chunks = pl.stage_seg_chunks;
-    /* measured on B200 (1M x 768 f32): per-lane issue 9.67 ms, single-lane back-to-back issue 10.33 ms */
-    a.issue_per_lane = (uint32_t)tune.issue_per_lane;
     return nullptr;
 }
 

@@ -47,7 +47,7 @@ struct launch_plan_t {
     bool maxed = false; /* growing the scratch any further cannot help */
     size_t visited_words_per_warp() const { return visited_bitmap_words ? visited_bitmap_words : visited_cap; }
     uint32_t smem_per_warp = 0, off_top_d = 0, off_top_s = 0, off_cand_s = 0, off_cand_d = 0, off_heap = 0;
-    uint32_t off_bars = 0, off_stage = 0, stage_stride = 0, stage_sets = 1, stage_segments = 1, stage_seg_chunks = 0;
+    uint32_t off_bars = 0, off_stage = 0, stage_stride = 0, stage_sets = 1;
     int blocks = 0;
     uint32_t warps_per_sm_target = 0;
     size_t smem_per_block = 0;
@@ -199,12 +199,11 @@ struct frozen_index_t {
     bool loaded = false;
     void* dev_allocs[8] = {nullptr};
 
-    /* tuning knobs of the search launch: environment at construction (USEARCH_B200_STAGE_SETS, _WARPS_PER_SM,
-     * _ISSUE_PER_LANE), changeable per handle with usearch_b200_tune (bench sweeps, tests) */
+    /* tuning knobs of the search launch: environment at construction (USEARCH_B200_STAGE_SETS, _WARPS_PER_SM),
+     * changeable per handle with usearch_b200_tune (bench sweeps, tests) */
     struct tune_t {
         int stage_sets = env_int("USEARCH_B200_STAGE_SETS", 0);     /* 0 = planned, 1 or 2 = forced */
         int warps_per_sm = env_int("USEARCH_B200_WARPS_PER_SM", 0); /* 0 = as many as fit, else an upper bound */
-        int issue_per_lane = env_int("USEARCH_B200_ISSUE_PER_LANE", 1);
         static int env_int(char const* name, int fallback) {
             char const* v = std::getenv(name);
             return v ? std::atoi(v) : fallback;

@@ -318,65 +318,44 @@ __device__ __noinline__ void measure_direct(device_index_t const& ix, warp_ctx_t
 
 /*
  *  STAGED: TMA bulk copies (cp.async.bulk, UBLKCP) land candidate vectors in shared-memory slots, LPV lanes
- *  then reduce each slot in the reference's summation order.
- *
- *  A vector may be fetched in `segs` SEGMENTS (1 or 2 copies of seg_chunks*16 bytes): with half-size
- *  slots almost twice as many warps fit on an SM (7 instead of 4 at 768 x f32), and with one warp per
- *  scheduler it is thread-level parallelism, not bandwidth, that the kernel is short of. The unit of
- *  work is a "segment pass" sp = pass * segs + h: segment h of candidates [pass*VPP, pass*VPP+VPP) goes to
- *  slot set sp % nsets, one mbarrier per set; the accumulators live across the segments of a pass, so
- *  the order of the fma chain is untouched.
+ *  then reduce each slot in the reference's summation order. A PASS = the next 32 / LPV candidates; pass p goes to slot set
+ *  p mod nsets (nsets = 1: fetch-then-reduce; 2: the next pass lands during the math), one mbarrier per set.
+ *  (Round 1 could also fetch a vector as two half-size segments for more resident warps; measured a wash, and the index
+ *  arithmetic it needed — divisions by run-time constants in this loop — showed up as 5 % of the kernel's issue slots in
+ *  ncu. Removed in round 2.)
  */
 template <class M>
 __device__ __forceinline__ void measure_staged(device_index_t const& ix, search_args_t const& a, warp_ctx_t& w,
                                                typename M::qconst_t qc, uint32_t ncand, int lane) {
     constexpr int LPV = M::LPV, VPP = 32 / LPV;
     int const g = lane / LPV, sub = lane % LPV;
-    uint32_t const chunks = ix.chunks16;
-    uint32_t const nsets = a.stage_sets; /* 1: fetch-then-reduce; 2: the next segment pass lands during the math */
-    uint32_t const segs = a.stage_segments, seg_chunks = a.stage_seg_chunks;
-    uint32_t const nsp = ((ncand + VPP - 1) / VPP) * segs;
-    /* `cp.async.bulk` takes uniform-register operands, so the per-lane issue is serialised by the compiler
-     * with an ELECT loop; lane 0 issuing all copies back to back measured 7 % slower end to end and is kept
-     * only as a tuning knob (`issue_per_lane == 0`). */
-    auto issue = [&](uint32_t sp) {
-        uint32_t const pass = sp / segs, h = sp - pass * segs;
-        uint32_t const base = pass * VPP, cnt = min((uint32_t)VPP, ncand - base), set = sp % nsets;
-        uint32_t const c0 = h * seg_chunks, bytes = (min(chunks, c0 + seg_chunks) - c0) * 16u;
+    bool const two_sets = a.stage_sets > 1;
+    uint32_t const npass = (ncand + VPP - 1) / VPP;
+    uint32_t const bytes = ix.chunks16 * 16u;
+    /* `cp.async.bulk` takes uniform-register operands, so the per-lane issue is serialised by the compiler with an ELECT
+     * loop; lane 0 issuing all copies back to back measured 7 % slower end to end (round 1). */
+    auto issue = [&](uint32_t pass) {
+        uint32_t const base = pass * VPP, cnt = min((uint32_t)VPP, ncand - base), set = two_sets ? (pass & 1u) : 0u;
         uint32_t const my_slot = (uint32_t)lane < cnt ? w.cand_s[base + lane] : 0u;
         uint32_t const bar = w.bars_addr + 8u * set;
         if (lane == 0) mbar_expect_tx(bar, cnt * bytes);
         __syncwarp();
-        if (a.issue_per_lane) {
-            if ((uint32_t)lane < cnt)
-                bulk_copy_g2s(w.stage_addr + (set * VPP + lane) * a.stage_stride,
-                              ix.vectors + (size_t)my_slot * ix.vec_stride + (size_t)c0 * 16u, bytes, bar);
-        } else {
-            for (uint32_t i = 0; i < cnt; ++i) {
-                uint32_t const slot = __shfl_sync(0xffffffffu, my_slot, (int)i);
-                if (lane == 0)
-                    bulk_copy_g2s(w.stage_addr + (set * VPP + i) * a.stage_stride,
-                                  ix.vectors + (size_t)slot * ix.vec_stride + (size_t)c0 * 16u, bytes, bar);
-            }
-        }
+        if ((uint32_t)lane < cnt)
+            bulk_copy_g2s(w.stage_addr + (set * VPP + lane) * a.stage_stride, ix.vectors + (size_t)my_slot * ix.vec_stride, bytes, bar);
     };
     issue(0);
-    if (nsets > 1 && nsp > 1) issue(1);
-    typename M::acc_t acc;
-    M::init(acc);
-    for (uint32_t sp = 0; sp < nsp; ++sp) {
-        uint32_t const pass = sp / segs, h = sp - pass * segs;
-        uint32_t const base = pass * VPP, cnt = min((uint32_t)VPP, ncand - base), set = sp % nsets;
-        uint32_t const c0 = h * seg_chunks, c1 = min(chunks, c0 + seg_chunks);
-        /* unit j of the vector (a 16-byte chunk, or a 32-bit word for the WORD metrics) sits at slot offset
-         * (j - c0 * UPC) * sizeof(unit) */
-        using U = typename unit_of<M>::type;
-        constexpr uint32_t UPC = unit_of<M>::UPC;
-        uint32_t const u0 = c0 * UPC, u1 = c1 * UPC;
-        U const* buf = reinterpret_cast<U const*>(w.stage + (size_t)(set * VPP + g) * a.stage_stride) - u0;
-        U const* qu = reinterpret_cast<U const*>(w.q4);
+    if (two_sets && npass > 1) issue(1);
+    /* unit j of the vector: a 16-byte chunk, or a 32-bit word for the WORD metrics */
+    using U = typename unit_of<M>::type;
+    constexpr uint32_t UPC = unit_of<M>::UPC;
+    uint32_t const u1 = ix.chunks16 * UPC;
+    U const* const qu = reinterpret_cast<U const*>(w.q4);
+    for (uint32_t pass = 0; pass < npass; ++pass) {
+        uint32_t const base = pass * VPP, cnt = min((uint32_t)VPP, ncand - base), set = two_sets ? (pass & 1u) : 0u;
+        U const* const buf = reinterpret_cast<U const*>(w.stage + (size_t)(set * VPP + g) * a.stage_stride);
         bool const act = (uint32_t)g < cnt;
-        if (h == 0) M::init(acc);
+        typename M::acc_t acc;
+        M::init(acc);
         if (a.phase_cycles) { /* introspection only: attribute the wait for the slowest slot to `vector_wait` */
             long long t = clock64();
             if (act) mbar_wait(w.bars_addr + 8u * set, (w.phase >> set) & 1u);
@@ -386,7 +365,7 @@ __device__ __forceinline__ void measure_staged(device_index_t const& ix, search_
         if (act) {
             if (!a.phase_cycles) mbar_wait(w.bars_addr + 8u * set, (w.phase >> set) & 1u);
             /* 4 steps per iteration, the next iteration's 8 shared-memory loads issued before this one's math */
-            uint32_t j = u0 + sub;
+            uint32_t j = (uint32_t)sub;
             if (j + 3 * LPV < u1) {
                 U b0 = buf[j], b1 = buf[j + LPV], b2 = buf[j + 2 * LPV], b3 = buf[j + 3 * LPV];
                 U q0 = qu[j], q1 = qu[j + LPV], q2 = qu[j + 2 * LPV], q3 = qu[j + 3 * LPV];
@@ -408,13 +387,12 @@ __device__ __forceinline__ void measure_staged(device_index_t const& ix, search_
             }
             for (; j < u1; j += LPV) M::step(acc, buf[j], qu[j]);
         }
-        if (h + 1 == segs) { /* last segment of the pass: horizontal reduce (warp-wide shuffles: every lane) */
-            float d = M::finish(acc, qc);
-            if (act && sub == 0) w.cand_d[base + g] = d;
-        }
+        float const d = M::finish(acc, qc); /* horizontal reduce (warp-wide shuffles: every lane) */
+        if (act && sub == 0) w.cand_d[base + g] = d;
         w.phase ^= 1u << set; /* one parity bit per set */
         __syncwarp();         /* every lane is done with this set before it is refilled */
-        if (sp + nsets < nsp) issue(sp + nsets);
+        uint32_t const next = pass + (two_sets ? 2u : 1u);
+        if (next < npass) issue(next);
     }
 }
 

@@ -501,7 +501,7 @@ class Index:
         return BatchMatches(keys, distances, counts, vm, cd)
 
     def tune(self, **knobs: int) -> None:
-        """Launch tuning knobs of this handle (stage_sets, warps_per_sm, issue_per_lane); results never change."""
+        """Launch tuning knobs of this handle (stage_sets, warps_per_sm); results never change."""
         for name, value in knobs.items():
             if self._lib.usearch_b200_tune(self._h, name.encode(), int(value)) != 0:
                 raise ValueError(f"unknown knob {name}")
