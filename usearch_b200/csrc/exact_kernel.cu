@@ -442,8 +442,7 @@ char const* exact_search_device(device_index_t const& ix, int sm_count, void con
                       (ix.metric == METRIC_IP || ix.metric == METRIC_L2SQ || ix.metric == METRIC_COS);
     if ((forced == 3 || forced == 4) && !imma) return "The tensor-core exact-search kernels serve i8 vectors only";
     /* tcgen05 (exact_umma.cu) when the driver can encode tensor maps; mma.sync (exact_imma.cu) otherwise or when forced */
-    bool const umma = imma && forced != 3 && exact_umma_usable(ix, a);
-    if (forced == 4 && !umma) return "The tcgen05 exact-search kernel is not usable here";
+    bool const umma = imma && forced != 3 && exact_umma_usable(ix, a); /* count <= 24; larger counts stay on mma.sync */
     bool const tiled = !imma && (forced == 1 && !big_k ? false : tiled_smem <= 227 * 1024);
     if (big_k && !tiled) return "Exact search with count > 256 needs vectors that fit the tiled stage";
     if (forced == 2 && !tiled) return "Vectors too long for the tiled exact-search stage";

@@ -204,6 +204,22 @@ __global__ void __launch_bounds__(UM_THREADS, 1) exact_umma_kernel(__grid_consta
         uint32_t* const ls = reinterpret_cast<uint32_t*>(ld - row * UM_LIST_STRIDE + UM_BM * UM_LIST_STRIDE) + row * UM_LIST_STRIDE;
         uint32_t size = 0;
         float worst = 0.f;
+        /* filter thresholds while the list is not full: everything passes */
+        int thr_i = INT32_MIN;
+        float thr_f = -__int_as_float(0x7f800000);
+        auto set_thresholds = [&]() { /* the list is full: a column can only enter with d <= worst */
+            /* slack: the int -> float conversions and the subtraction round by at most 1.5 ulp of the sum's magnitude
+             * (sums beyond 2^24 are not exact in f32); 4 ulps + 4 units are allowed for */
+            if constexpr (METRIC == METRIC_IP) { /* d = 1 - float(ab), non-increasing in ab */
+                float const t = __fsub_rd(1.0f, worst);
+                thr_i = __float2int_rd(t - fabsf(t) * 4.8e-7f) - 4;
+            } else if constexpr (METRIC == METRIC_L2SQ) /* d = float(a2 + b2 - 2ab) <= worst  <=>  2ab - b2 >= a2 - floor(worst) (- slack) */
+                thr_i = qa2 - (__float2int_ru(worst + fabsf(worst) * 4.8e-7f) + 4);
+            else { /* d = 1 - ab*qr*vr <= worst  <=>  ab*vr >= (1 - worst) / qr, lowered by a relative 1e-5 */
+                float const base = __fdiv_rn(__fsub_rn(1.0f, worst), qr);
+                thr_f = base - fabsf(base) * 1e-5f - 1e-30f;
+            }
+        };
         for (uint32_t t = 0; t < ntiles; ++t) {
             uint32_t const buf = t & 1u, buf_phase = (t >> 1) & 1u, tile_base = seg_lo + t * UM_BN;
             /* per-column facts of this tile (two columns per thread), while the MMAs run */
@@ -223,15 +239,30 @@ __global__ void __launch_bounds__(UM_THREADS, 1) exact_umma_kernel(__grid_consta
             for (uint32_t c0 = 0; c0 < UM_BN; c0 += 32) {
                 int v[32];
                 tmem_ld32(tmem_base + ((quarter * 32u) << 16) + buf * UM_BN + c0, v);
-                uint32_t const mask = col_mask[buf][c0 >> 5];
-                if (live && mask) {
+                /* FILTER, branch-free: which of the 32 columns could still enter this row's list? A conservative test on
+                 * the integer dot product (never misses a candidate, may flag a few too many); the first version ran the
+                 * exact float test with two branches per element and spent 17 warp instructions per column (ncu). */
+                uint32_t pm = 0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    bool maybe;
+                    if constexpr (METRIC == METRIC_IP) maybe = v[j] >= thr_i;
+                    else if constexpr (METRIC == METRIC_L2SQ) maybe = 2 * v[j] - col_b2[buf][c0 + j] >= thr_i;
+                    else maybe = !(__int2float_rn(v[j]) * col_rn[buf][c0 + j] < thr_f); /* a NaN (zero vector) passes */
+                    pm |= maybe ? (1u << j) : 0u;
+                }
+                pm &= col_mask[buf][c0 >> 5];
+                if (live && pm) { /* rare: the exact metric and the sorted insert for the flagged columns */
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        if (!((mask >> j) & 1u)) continue;
+                        if (!((pm >> j) & 1u)) continue;
                         float const d = i8_distance<METRIC, SWAP>(v[j], qa2, col_b2[buf][c0 + j], qr, col_rn[buf][c0 + j]);
                         if (size < a.k || !(d > worst)) {
                             list_insert(ld, ls, size, a.k, d, tile_base + c0 + (uint32_t)j);
-                            if (size == a.k) worst = ld[a.k - 1];
+                            if (size == a.k) {
+                                worst = ld[a.k - 1];
+                                set_thresholds();
+                            }
                         }
                     }
                 }
