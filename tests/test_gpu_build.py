@@ -237,3 +237,28 @@ def test_enqueue_then_finish_equals_the_blocking_calls():
     env = dict(os.environ, USEARCH_B200_VISITED="hash", USEARCH_B200_SCRATCH_SHRINK="64")
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "ENQUEUE_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_adding_to_a_loaded_reference_built_index():
+    """`load` a file written by the reference, then keep adding on the GPU (capacity grows from the file's size), save, and
+    let the reference search the result: every member, old and new, is its own nearest neighbour."""
+    from usearch_b200.index import Index
+    n0, n1, d = 4000, 3000, 64
+    base, _ = common.make_collection(n0 + n1, d, "f32", 1)
+    ref, blob = common.build_reference_blob(base[:n0], "cos", "f32", d, 16, threads=8)
+    index = Index.restore(blob)
+    assert len(index) == n0
+    index.add(np.arange(n0, n0 + n1, dtype=np.uint64), base[n0:])
+    assert len(index) == n0 + n1
+    rep = structure_report(index.save())
+    assert rep["n_problems"] == 0, rep["problems"]
+    searcher = bindings.RefIndex("parity")
+    searcher.load(index.save())
+    searcher.change_expansion_search(64)
+    keys, dist, _, _, _ = searcher.search(base, 1, threads=16)
+    assert (keys[:, 0] == np.arange(n0 + n1, dtype=np.uint64)).mean() > 0.995
+    # clear -> the handle is reusable for a new collection
+    index.clear()
+    assert len(index) == 0
+    index.add(np.arange(100, dtype=np.uint64), base[:100])
+    assert len(index) == 100 and index.contains(99)
