@@ -31,6 +31,7 @@ sys.path.insert(0, ROOT)
 from usearch_b200 import datagen  # noqa: E402
 
 METRIC = "QPS @ recall@10>=0.95"
+_REAL_STDOUT = sys.stdout
 CHUNK = 262144  # rows generated at a time; chunk c of a collection is a pure function of (seed, c)
 WORKLOADS = {  # BASELINE.json configs + the configuration its metric is quoted on (NS)
     "NS": dict(n=10_000_000, dim=768, metric="cos", dtype="f32", connectivity=32, ef=128, batch=4096),
@@ -365,7 +366,7 @@ def run_reference_arm(a):
                          "sample": f"{a.steps} batches of {a.batch} queries, reference built -O3 -ffast-math -march=native, SimSIMD {ref.isa_name}"},
         "e2e": {"value": round(qps, 1), "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_REAL_STDOUT, flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -679,9 +680,11 @@ def run_b200_arm(a):
                      "formula": "sum_q D_q*bytes_per_vector + H_q*(4+4*M0), D/H = the reference's computed_distances/visited_members; rank 0's launch"},
         "cpu_baseline": cpu,
     }
+    if shards > 1:  # what the exchange step costs: the step minus this rank's search kernel
+        line["config"]["exchange_ms_per_step"] = round(elapsed_ms / K - k_ms, 3)
     if next_rows:
         line["next_rows"] = next_rows
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_REAL_STDOUT, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -689,6 +692,12 @@ def run_b200_arm(a):
 
 def main():
     a = parse_args()
+    # The contract is ONE JSON line on stdout. Libraries (NCCL prints its version on fd 1 at communicator creation) must not
+    # get in its way: everything that writes to fd 1 goes to stderr, only the JSON line goes to the real stdout.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if a.impl == "reference":
         run_reference_arm(a)
     else:
