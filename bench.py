@@ -243,6 +243,15 @@ def recall_at_k(found_keys: np.ndarray, counts: np.ndarray, truth: np.ndarray) -
     return hits / float(truth.size)
 
 
+def recall_at_k_with_ties(found_d: np.ndarray, counts: np.ndarray, truth_d: np.ndarray) -> float:
+    """Binary codes have 257 possible Hamming distances: the k-th neighbour is usually one of many at the same distance and
+    set intersection punishes an arbitrary choice among them. Here a found entry counts when its distance does not exceed the
+    true k-th smallest distance (both sides count the same integer)."""
+    kth = truth_d[:, -1:]
+    ok = (found_d <= kth + 0.25) & (np.arange(found_d.shape[1])[None, :] < counts[:, None])
+    return float(ok.sum()) / float(truth_d.size)
+
+
 def to_numpy_queries(a, q):
     """Device query tensor -> the host array the C ABI / the reference take (bf16 travels as uint16)."""
     import torch
@@ -491,7 +500,11 @@ def run_b200_arm(a):
     cnt_dev = torch.zeros(B, dtype=torch.int32, device=device)
     comp_dev = torch.zeros(B, dtype=torch.int32, device=device)
     vis_dev = torch.zeros(B, dtype=torch.int32, device=device)
-    stream = torch.cuda.current_stream(device)
+    # An explicit stream for everything that follows: the library launches on the stream it is given (0 / the legacy default
+    # stream would mean "the handle's own stream", which torch's events and copies are not ordered with).
+    stream = torch.cuda.Stream(device)
+    torch.cuda.synchronize(device)
+    torch.cuda.set_stream(stream)
     search_device = index.sharded_search_device if shards > 1 else index.search_device
 
     def step_device(s: int):
@@ -571,6 +584,10 @@ def run_b200_arm(a):
     gt_k, gt_d = exact_topk_gpu(a, coll, q0, k)
     found_k, found_d, found_c = first_found
     recall = recall_at_k(found_k.cpu().numpy().astype(np.uint64)[:R], found_c.cpu().numpy()[:R], gt_k.cpu().numpy().astype(np.uint64))
+    recall_ties = None
+    if a.dtype == "b1":
+        recall_ties = recall_at_k_with_ties(found_d.cpu().numpy()[:R], found_c.cpu().numpy()[:R], gt_d.cpu().numpy())
+    log(f"rank {rank}: recall@{k} of its first timed batch ({R} rows) = {recall:.4f}; row 0 found {found_k[0].tolist()} truth {gt_k[0].tolist()}")
     if world > 1:  # every rank checks its own batch (replicas) or the same merged batch (shards)
         rt = torch.tensor([recall], device=device)
         dist.all_reduce(rt, op=dist.ReduceOp.MIN)
@@ -667,6 +684,7 @@ def run_b200_arm(a):
             "computed_distances_per_query": round(d_per_q, 1), "visited_members_per_query": round(h_per_q, 1),
         },
         "recall_at_10": round(recall, 4),
+        **({"recall_at_10_counting_ties": round(recall_ties, 4)} if recall_ties is not None else {}),
         "gpu_launches": int(launches),
         "clocks": clocks,
         "e2e": {"value": round(queries_per_step * K / e2e_s, 1), "unit": "queries/s", "h2d_bytes_per_step": int(B * bpv),

@@ -179,7 +179,9 @@ void usearch_b200_shards_join(usearch_index_t index, int rank, int world, void c
 size_t usearch_b200_sharded_search_many(usearch_index_t index, void const* queries, size_t queries_count, size_t queries_stride,
                                         usearch_scalar_kind_t query_kind, size_t count, usearch_key_t* keys,
                                         usearch_distance_t* distances, size_t* counts, usearch_error_t* error);
-/* device pointers, queries already in the index's scalar kind (see usearch_b200_search_many_device) */
+/* device pointers, queries already in the index's scalar kind (see usearch_b200_search_many_device). With a `cuda_stream` the
+ * all-gather and the merge are only ENQUEUED on it (the outputs are ready in stream order); with NULL the call uses the handle's
+ * own stream and returns when the merged rows are complete. */
 void usearch_b200_sharded_search_many_device(usearch_index_t index, void const* queries, size_t queries_count,
                                              size_t queries_stride, size_t count, usearch_key_t* keys,
                                              usearch_distance_t* distances, uint32_t* counts, uint32_t* computed_distances,

@@ -52,7 +52,9 @@ def main():
     cnt = torch.zeros(B, dtype=torch.int32, device=device)
     comp = torch.zeros(B, dtype=torch.int32, device=device)
     vis = torch.zeros(B, dtype=torch.int32, device=device)
-    stream = torch.cuda.current_stream(device)
+    stream = torch.cuda.Stream(device)
+    torch.cuda.synchronize(device)
+    torch.cuda.set_stream(stream)
     peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
     R = min(B, 1024)
     gt, _ = bench.exact_topk_gpu(a, coll, q_dev[:R], k)

@@ -515,8 +515,11 @@ void usearch_b200_sharded_search_many_device(usearch_index_t index, void const* 
     std::lock_guard<std::mutex> lock(ix->mutex);
     if (char const* e = ix->ensure_context()) return set_error(error, e);
     cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ix->stream;
-    set_error(error, ix->sharded_search_device(queries, queries_count, queries_stride, count, keys, distances, counts,
-                                               computed_distances, visited_members, s));
+    char const* e = ix->sharded_search_device(queries, queries_count, queries_stride, count, keys, distances, counts,
+                                              computed_distances, visited_members, s);
+    /* on the handle's own stream the caller has nothing to order its next use of the outputs with: finish before returning */
+    if (!e && !cuda_stream && cudaStreamSynchronize(s) != cudaSuccess) e = "CUDA failure: synchronize";
+    set_error(error, e);
 }
 
 size_t usearch_b200_shards_payload_bytes(size_t queries_count, size_t count) { return shards_payload_bytes(queries_count, count); }
