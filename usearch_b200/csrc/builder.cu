@@ -551,6 +551,8 @@ char const* frozen_index_t::reserve_slots(size_t slots) {
     if (char const* e = ensure_context()) return e;
     if (!configured()) return "Index is not initialized: call usearch_init with options or load a file first";
     if (slots >= 0xFFFFFFFFull) return "Too many entries for 32-bit slots";
+    if (connectivity_base >= LINK_CAND_MAX || connectivity > connectivity_base)
+        return "Connectivity too large for the GPU builder (a list plus one arrival must fit 256 candidates)";
     if (!loaded) { /* first reservation of an index made by usearch_init(options): the empty layout */
         device_index_t ix;
         ix.m = (uint32_t)connectivity;
@@ -715,7 +717,21 @@ char const* frozen_index_t::add_many(uint64_t const* new_keys, void const* vecto
         /* a member above the current top level ends its batch: the next batch descends from it */
         for (size_t i = 0; i < batch; ++i)
             if (levels[at + i] > d.max_level) { batch = i + 1; break; }
-        if (char const* e = link_batch(at, batch)) return e;
+        if (char const* e = link_batch(at, batch)) {
+            /* members that were stored but not linked are dropped again: the index stays what the graph says it is */
+            size_t rows_kept = 0;
+            for (size_t i = 0; i < (size_t)d.n; ++i) rows_kept += (size_t)levels[i];
+            size = d.n;
+            host_keys.resize(size);
+            levels.resize(size);
+            upper_rows = rows_kept;
+            key_map.clear();
+            cudaMemsetAsync(const_cast<uint32_t*>(d.nbr0) + size * d.m0_stride, 0xFF, (first + count - size) * d.m0_stride * 4, stream);
+            if (upper_capacity > upper_rows)
+                cudaMemsetAsync(const_cast<uint32_t*>(d.upper) + upper_rows * d.m_stride, 0xFF, (upper_capacity - upper_rows) * d.m_stride * 4, stream);
+            cudaStreamSynchronize(stream);
+            return e;
+        }
         at += batch;
     }
     return nullptr;
