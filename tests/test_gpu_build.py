@@ -77,6 +77,9 @@ def test_incremental_adds_grow_the_index_and_find_themselves():
     assert float(np.nanmax(res.distances[:, 0])) < 1e-5
     with pytest.raises(RuntimeError, match="Duplicate"):
         index.add(7, base[3])
+    with pytest.raises(RuntimeError, match="Duplicate"):   # twice within one call
+        index.add(np.array([777777, 777777], dtype=np.uint64), base[3:5])
+    assert len(index) == n and not index.contains(777777)
     # f64 input is cast on the device; the round trip through `get` returns the stored f32
     index.add(99999, base[5].astype(np.float64))
     assert np.array_equal(index.get(99999), base[5])

@@ -643,6 +643,11 @@ char const* frozen_index_t::add_many(uint64_t const* new_keys, void const* vecto
         build_key_map();
         for (size_t i = 0; i < count; ++i)
             if (key_map.contains(hk[i])) return "Duplicate keys not allowed in high-level wrappers";
+        if (count > 1) { /* ... nor twice within one call: the reference would refuse the second `add` */
+            std::vector<uint64_t> sorted(hk, hk + count);
+            std::sort(sorted.begin(), sorted.end());
+            if (std::adjacent_find(sorted.begin(), sorted.end()) != sorted.end()) return "Duplicate keys not allowed in high-level wrappers";
+        }
     }
     size_t const src_bytes = (dimensions * bits_per_scalar(kind) + 7) / 8;
     if (stride == 0) stride = src_bytes;

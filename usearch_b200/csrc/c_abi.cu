@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <cstring>
 #include <new>
+#include <utility>
 #include <vector>
 
 #include "../../include/usearch_b200.h"
@@ -78,8 +79,23 @@ usearch_scalar_kind_t scalar_to_c(uint32_t c) { /* c/lib.cpp:69-79 */
 
 frozen_index_t* as_index(usearch_index_t h) { return reinterpret_cast<frozen_index_t*>(h); }
 
+/* nothing may propagate through the C boundary: host containers can throw std::bad_alloc */
+template <class F> char const* guarded(F&& f) {
+    try {
+        return f();
+    } catch (std::bad_alloc const&) {
+        return "Out of memory!";
+    } catch (...) {
+        return "Unexpected failure inside the library";
+    }
+}
+
 void set_error(usearch_error_t* error, char const* message) {
     if (error && message) *error = message;
+}
+
+template <class... A> char const* search_host_guarded(frozen_index_t* ix, A&&... args) {
+    return guarded([&] { return search_host_guarded(ix, std::forward<A>(args)...); });
 }
 
 /* read-only mapping of a file, handed to load_blob */
@@ -170,13 +186,13 @@ char const* usearch_hardware_acceleration(usearch_index_t, usearch_error_t*) { r
 size_t usearch_serialized_length(usearch_index_t index, usearch_error_t*) { return as_index(index)->serialized_length(); }
 
 void usearch_save_buffer(usearch_index_t index, void* buffer, size_t length, usearch_error_t* error) {
-    set_error(error, as_index(index)->save_blob(static_cast<uint8_t*>(buffer), length));
+    set_error(error, guarded([&] { return as_index(index)->save_blob(static_cast<uint8_t*>(buffer), length); }));
 }
 
 void usearch_load_buffer(usearch_index_t index, void const* buffer, size_t length, usearch_error_t* error) {
     frozen_index_t* ix = as_index(index);
     std::lock_guard<std::mutex> lock(ix->mutex);
-    set_error(error, ix->load_blob(static_cast<uint8_t const*>(buffer), length));
+    set_error(error, guarded([&] { return ix->load_blob(static_cast<uint8_t const*>(buffer), length); }));
 }
 
 void usearch_view_buffer(usearch_index_t index, void const* buffer, size_t length, usearch_error_t* error) {
@@ -221,7 +237,7 @@ size_t usearch_connectivity(usearch_index_t index, usearch_error_t*) { return as
 void usearch_reserve(usearch_index_t index, size_t capacity, usearch_error_t* error) { /* c/lib.cpp:365-370 */
     frozen_index_t* ix = as_index(index);
     std::lock_guard<std::mutex> lock(ix->mutex);
-    set_error(error, ix->reserve_slots(capacity));
+    set_error(error, guarded([&] { return ix->reserve_slots(capacity); }));
 }
 size_t usearch_expansion_add(usearch_index_t index, usearch_error_t*) { return as_index(index)->expansion_add; }
 size_t usearch_expansion_search(usearch_index_t index, usearch_error_t*) { return as_index(index)->expansion_search; }
@@ -252,7 +268,7 @@ size_t usearch_search(usearch_index_t index, void const* query, usearch_scalar_k
     if (!qs) { set_error(error, "Unknown scalar kind!"); return 0; }
     size_t total = 0;
     /* concurrent single-query callers are coalesced into one launch (frozen_index_t::search_single) */
-    if (char const* e = ix->search_single(query, qs, count, keys, distances, &total)) {
+    if (char const* e = guarded([&] { return ix->search_single(query, qs, count, keys, distances, &total); })) {
         set_error(error, e);
         return 0;
     }
@@ -276,7 +292,7 @@ size_t usearch_filtered_search(usearch_index_t index, void const* query, usearch
             if (key != ix->free_key && filter(key, filter_state)) allowed.push_back(key);
     }
     size_t total = 0;
-    if (char const* e = ix->search_host(query, 1, 0, qs, count, keys, count * 8, distances, count * 4, nullptr, nullptr,
+    if (char const* e = search_host_guarded(ix, query, 1, 0, qs, count, keys, count * 8, distances, count * 4, nullptr, nullptr,
                                         nullptr, &total, allowed.data(), allowed.size(), true)) {
         set_error(error, e);
         return 0;
@@ -291,7 +307,7 @@ size_t usearch_search_many(usearch_index_t index, void const* queries, size_t qu
     uint32_t qs = scalar_to_char(query_kind);
     if (!qs) { set_error(error, "Unknown scalar kind!"); return 0; }
     size_t total = 0;
-    if (char const* e = ix->search_host(queries, queries_count, queries_stride, qs, count, keys, keys_stride, distances,
+    if (char const* e = search_host_guarded(ix, queries, queries_count, queries_stride, qs, count, keys, keys_stride, distances,
                                         distances_stride, counts, nullptr, nullptr, &total)) {
         set_error(error, e);
         return 0;
@@ -307,7 +323,7 @@ size_t usearch_b200_search_many_stats(usearch_index_t index, void const* queries
     uint32_t qs = scalar_to_char(query_kind);
     if (!qs) { set_error(error, "Unknown scalar kind!"); return 0; }
     size_t total = 0;
-    if (char const* e = ix->search_host(queries, queries_count, queries_stride, qs, count, keys, count * 8, distances,
+    if (char const* e = search_host_guarded(ix, queries, queries_count, queries_stride, qs, count, keys, count * 8, distances,
                                         count * 4, counts, computed_distances, visited_members, &total)) {
         set_error(error, e);
         return 0;
@@ -324,7 +340,7 @@ size_t usearch_b200_filtered_search_many(usearch_index_t index, void const* quer
     uint32_t qs = scalar_to_char(query_kind);
     if (!qs) { set_error(error, "Unknown scalar kind!"); return 0; }
     size_t total = 0;
-    if (char const* e = ix->search_host(queries, queries_count, queries_stride, qs, count, keys, count * 8, distances,
+    if (char const* e = search_host_guarded(ix, queries, queries_count, queries_stride, qs, count, keys, count * 8, distances,
                                         count * 4, counts, computed_distances, visited_members, &total, allowed_keys,
                                         allowed_count, true)) {
         set_error(error, e);
@@ -371,7 +387,7 @@ void usearch_add(usearch_index_t index, usearch_key_t key, void const* vector, u
     uint32_t const vs = scalar_to_char(kind);
     if (!vs) return set_error(error, "Unknown scalar kind!");
     std::lock_guard<std::mutex> lock(ix->mutex);
-    set_error(error, ix->add_many(&key, vector, 1, 0, vs, false));
+    set_error(error, guarded([&] { return ix->add_many(&key, vector, 1, 0, vs, false); }));
 }
 
 void usearch_b200_add_many(usearch_index_t index, usearch_key_t const* keys, void const* vectors, size_t count, size_t vectors_stride,
@@ -380,7 +396,7 @@ void usearch_b200_add_many(usearch_index_t index, usearch_key_t const* keys, voi
     uint32_t const vs = scalar_to_char(kind);
     if (!vs) return set_error(error, "Unknown scalar kind!");
     std::lock_guard<std::mutex> lock(ix->mutex);
-    set_error(error, ix->add_many(keys, vectors, count, vectors_stride, vs, false));
+    set_error(error, guarded([&] { return ix->add_many(keys, vectors, count, vectors_stride, vs, false); }));
 }
 
 void usearch_b200_add_many_device(usearch_index_t index, usearch_key_t const* keys, void const* vectors, size_t count,
@@ -389,7 +405,7 @@ void usearch_b200_add_many_device(usearch_index_t index, usearch_key_t const* ke
     uint32_t const vs = scalar_to_char(kind);
     if (!vs) return set_error(error, "Unknown scalar kind!");
     std::lock_guard<std::mutex> lock(ix->mutex);
-    set_error(error, ix->add_many(keys, vectors, count, vectors_stride, vs, true));
+    set_error(error, guarded([&] { return ix->add_many(keys, vectors, count, vectors_stride, vs, true); }));
 }
 
 bool usearch_contains(usearch_index_t index, usearch_key_t key, usearch_error_t*) { /* c/lib.cpp:388-391 */
@@ -413,7 +429,7 @@ size_t usearch_get(usearch_index_t index, usearch_key_t key, size_t count, void*
     if (!vs) { set_error(error, "Unknown scalar kind!"); return 0; }
     std::lock_guard<std::mutex> lock(ix->mutex);
     size_t found = 0;
-    set_error(error, ix->get_vectors(key, count, vectors, vs, &found));
+    set_error(error, guarded([&] { return ix->get_vectors(key, count, vectors, vs, &found); }));
     return found;
 }
 
@@ -421,7 +437,7 @@ size_t usearch_remove(usearch_index_t index, usearch_key_t key, usearch_error_t*
     frozen_index_t* ix = as_index(index);
     std::lock_guard<std::mutex> lock(ix->mutex);
     size_t removed = 0;
-    set_error(error, ix->remove_key(key, &removed));
+    set_error(error, guarded([&] { return ix->remove_key(key, &removed); }));
     return removed;
 }
 
@@ -429,7 +445,7 @@ size_t usearch_rename(usearch_index_t index, usearch_key_t from, usearch_key_t t
     frozen_index_t* ix = as_index(index);
     std::lock_guard<std::mutex> lock(ix->mutex);
     size_t renamed = 0;
-    set_error(error, ix->rename_key(from, to, &renamed));
+    set_error(error, guarded([&] { return ix->rename_key(from, to, &renamed); }));
     return renamed;
 }
 
@@ -461,7 +477,7 @@ void usearch_b200_cluster_many(usearch_index_t index, void const* queries, size_
     frozen_index_t* ix = as_index(index);
     uint32_t qs = scalar_to_char(query_kind);
     if (!qs) return set_error(error, "Unknown scalar kind!");
-    set_error(error, ix->search_host(queries, queries_count, queries_stride, qs, 1, keys, 8, distances, 4, nullptr, computed_distances,
+    set_error(error, search_host_guarded(ix, queries, queries_count, queries_stride, qs, 1, keys, 8, distances, 4, nullptr, computed_distances,
                                      visited_members, nullptr, nullptr, 0, false, (int)std::min<size_t>(level, 0x7FFF)));
 }
 
