@@ -77,3 +77,19 @@ def test_load_fails_loudly_without_cuda_device():
     g = np.load(os.path.join(common.GOLDEN, "cos_f32_n2000_d64.npz"))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         Index.restore(g["blob"])
+
+
+def test_searching_an_empty_index_returns_no_matches_without_a_device():
+    """index_gt::search on an empty index: zero matches, padded rows, no error (index.hpp:3036-3037) — answered on the host,
+    so this also runs on a box without a GPU and exercises every search entry of the C ABI."""
+    from usearch_b200.index import Index
+    index = Index(ndim=8, metric="cos", dtype="f32")
+    q = np.ones((3, 8), dtype=np.float32)
+    for res in (index.search(q, 4), index.search(q, 4, stats=True), index.search(q, 4, exact=True)):
+        assert res.counts.tolist() == [0, 0, 0] and (res.keys == 0).all() and np.isnan(res.distances).all()
+        assert (res.distances.view(np.uint32) == 0x7FA00000).all()   # the signalling NaN of dump_to
+    assert len(index.search(q[0], 4)) == 0
+    assert len(index.search(q[0].astype(np.float64), 4)) == 0
+    with pytest.raises(RuntimeError, match="No clusters"):
+        index.cluster(q, 1)
+    assert not index.contains(1) and index.count(1) == 0 and index.get(1) is None and index.remove(1) == 0 and index.rename(1, 2) == 0

@@ -95,7 +95,7 @@ void set_error(usearch_error_t* error, char const* message) {
 }
 
 template <class... A> char const* search_host_guarded(frozen_index_t* ix, A&&... args) {
-    return guarded([&] { return search_host_guarded(ix, std::forward<A>(args)...); });
+    return guarded([&] { return ix->search_host(std::forward<A>(args)...); });
 }
 
 /* read-only mapping of a file, handed to load_blob */

@@ -14,11 +14,13 @@
  *  How the work is laid out on the GPU is new:
  *    - a persistent grid (a multiple of the SM count, one warp per CTA) pulls query ids from one
  *      atomic counter;
- *    - the per-query state lives in shared memory: the query itself (read ~D times), `top`
- *      (sorted, maintained by the whole warp with ballots), the head of the `next` heap (its
- *      deep levels spill to a per-warp slab in HBM), the hop's candidate list;
- *    - `visits` is an open-addressing table in a per-warp slab of HBM driven with atomicCAS at
- *      L2, so that the 32 lanes test-and-set a whole neighbour list at once;
+ *    - the per-query state lives on chip: the query itself (read ~D times), the head of the `next`
+ *      heap (its deep levels spill to a per-warp slab in HBM) and the hop's candidate list in shared
+ *      memory, `top` in registers (8 entries per lane, sorted, maintained with ballots and shuffles;
+ *      shared memory beyond ef = 256);
+ *    - `visits` is a per-warp bitmap over all slots in HBM/L2 driven with atomicOr (an open-addressing
+ *      table driven with atomicCAS where the bitmaps would not fit the scratch budget), so that the 32
+ *      lanes test-and-set a whole neighbour list at once;
  *    - the neighbour vectors of a hop are fetched together. STAGED kernels (vectors >= 256 B) issue
  *      one TMA bulk copy (cp.async.bulk, UBLKCP) per candidate vector into a shared-memory slot and
  *      wait on its mbarrier: eight whole vectors are in flight per warp without holding a single
@@ -26,6 +28,8 @@
  *      kernels (short vectors: binary codes) stream 16-byte chunks through registers instead;
  *    - only the accept/insert replay that follows is sequential, as the reference's inner loop is,
  *      and it only visits the candidates that can still pass the radius test.
+ *  The same kernel, instantiated with INSERT = true, is search_to_insert_ (index.hpp:4010-4079) for the
+ *  batched builder (builder.cu): a work item per (new member, level), best-first on that level's lists.
  */
 #include <cuda_runtime.h>
 
