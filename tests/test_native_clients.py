@@ -60,3 +60,13 @@ def test_half_words_summation_order(tmp_path):
                     os.path.join(common.ROOT, "tests", "native", "test_half_words_order.c"), "-o", str(exe), "-lm"], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
     assert "HALF_WORDS_ORDER_OK" in out
+
+
+def test_key_map_native(tmp_path):
+    """The host-side key -> slot table (contains / count / get / remove / rename of the C ABI) as a plain C++11 unit test:
+    a multi-index with removed entries, growth from a wrong size hint, erase and re-probe, against std::multimap."""
+    exe = tmp_path / "key_map"
+    subprocess.run(["g++", "-std=c++11", "-O1", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(common.ROOT, "usearch_b200", "csrc"),
+                    os.path.join(NATIVE, "test_key_map.cpp"), "-o", str(exe)], check=True, capture_output=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    assert "KEY_MAP_OK" in out
